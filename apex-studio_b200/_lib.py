@@ -1,0 +1,60 @@
+"""ctypes loader for libapex_b200.so -- the C ABI declared in include/apex_b200.h.
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C apex-studio_b200/csrc``) so it
+travels with the repository snapshot.  There is no fallback: if the shared object is missing every op
+raises (the north star forbids CPU / library fallbacks).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapex_b200.so")
+
+_i, _i64, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/apex_b200.h declares.
+SIGNATURES = {
+    "b200_version": (_i, []),
+    "b200_strerror": (ctypes.c_char_p, [_i]),
+    "b200_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p]),
+    "b200_linear": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
+    "b200_layernorm_modulate": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i64, _i64, _f, _p]),
+    "b200_rmsnorm_rope": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p]),
+    "b200_gate_residual": (_i, [_p, _p, _p, _i, _i, _i64, _i64, _p]),
+    "b200_cfg_combine": (_i, [_p, _p, _p, _f, _i64, _p]),
+}
+
+B200_OK = 0
+_VALUE_ERRORS = {-1, -2, -6}  # shape / alignment / argument -> ValueError (as functions.py:791-801 raises)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the library; raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C apex-studio_b200/csrc). There is no CPU or library fallback for this path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code == B200_OK:
+        return
+    msg = load().b200_strerror(code).decode()
+    if code in _VALUE_ERRORS:
+        raise ValueError(f"{what}: {msg} (code {code})")
+    raise RuntimeError(f"{what}: {msg} (code {code})")

@@ -1,0 +1,352 @@
+// b200_attn_fwd: o = softmax(q k^T * scale) v  (non-causal, no mask), head_dim 128, bf16 in/out.
+//
+// One CTA owns TWO 128-row query tiles of one (batch, head) and streams all key/value tiles past them:
+//   warps 0-3   softmax for query tile 0 (one query row per thread, row == TMEM lane)
+//   warps 4-7   softmax for query tile 1
+//   warp  8     TMA producer: Q once, then K_j, V_j through a ring of 32 KB slots (128B-swizzled tiles)
+//   warp  9     MMA issuer:   S_t = Q_t K_j^T  (tcgen05.mma, A and B from shared memory, fp32 S in TMEM)
+//                             O_t += P_t V_j   (A = bf16 P read straight from TMEM, B = V MN-major in smem)
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_t overwrites the first 64 columns of S_t.
+// The issue order  PV0(j) S0(j+1) PV1(j) S1(j+1)  lets the tensor pipe work on one query tile while the
+// other tile's softmax runs, and makes "S_t(j+1) ready" imply "PV_t(j) finished", so the softmax warps
+// can rescale O_t in place (lazily, only when the running max grows by more than 2^8) without a
+// separate correction stage.
+//
+// Replaces attention_register.call(q, k, v) -- attention/functions.py:84 (`sdpa` :338-377 is the gold
+// backend) as called by transformer/wan/base/attention.py:397.
+#include "host_util.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+namespace attn {
+
+constexpr int D = 128;
+constexpr int BQ = 128;   // rows per query tile
+constexpr int BKV = 128;  // keys per tile
+constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two [128 x 64] swizzled half tiles
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+constexpr int KV_SLOTS = 4;
+constexpr int NUM_THREADS = 320;
+constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct Params {
+  int B, H, Sq, Sk;
+  __nv_bfloat16* o;
+  int64_t o_sb, o_sh, o_ss;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                      // 2 tiles
+  uint8_t* kv_smem = smem + 2 * TILE_BYTES;    // KV_SLOTS tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KV_SLOTS * TILE_BYTES);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* kv_full = bars + 1;            // [KV_SLOTS]
+  uint64_t* kv_empty = kv_full + KV_SLOTS; // [KV_SLOTS]
+  uint64_t* s_full = kv_empty + KV_SLOTS;  // [2]
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* o_done = p_full + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_block = blockIdx.x;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_kv = (p.Sk + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_SLOTS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_done[t], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+      for (int t = 0; t < 2; ++t) {
+        const int row0 = q_block * (2 * BQ) + t * BQ;
+        tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
+        tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        for (int kv = 0; kv < 2; ++kv) {
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          uint8_t* dst = kv_smem + slot * TILE_BYTES;
+          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+          mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+          tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV, head, batch);
+          tma_load_4d(dst + HALF_BYTES, tm, &kv_full[slot], 64, j * BKV, head, batch);
+          if (++slot == KV_SLOTS) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ, BKV, 0);  // B = K tile, K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ, D, 1);    // B = V tile, MN-major
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+      auto issue_s = [&](int t, int slot) {
+        const uint32_t a0 = q_addr + t * TILE_BYTES;
+        const uint32_t b0 = kv_addr + slot * TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+          umma_ss(tmem_base + t * 128, make_smem_desc_sw128(a0 + off, 16, 1024),
+                  make_smem_desc_sw128(b0 + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int slot, bool first) {
+        const uint32_t b0 = kv_addr + slot * TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
+                  make_smem_desc_sw128(b0 + kk * 2048, HALF_BYTES, 1024), idesc_o, (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      int slot = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++slot == KV_SLOTS) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(q_full, 0);
+      // prologue: S0(0), S1(0)
+      mbar_wait(&kv_full[slot], phase);
+      tc_fence_after();
+      issue_s(0, slot);
+      umma_commit(&s_full[0]);
+      issue_s(1, slot);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[slot]);
+      advance();
+      for (int j = 0; j < n_kv; ++j) {
+        const int v_slot = slot;
+        const uint32_t v_phase = phase;
+        advance();
+        const int k_slot = slot;  // K_{j+1}
+        const uint32_t k_phase = phase;
+        const bool has_next = (j + 1 < n_kv);
+        if (has_next) advance();
+
+        mbar_wait(&kv_full[v_slot], v_phase);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, v_slot, j == 0);
+        umma_commit(&o_done[0]);
+        if (has_next) {
+          mbar_wait(&kv_full[k_slot], k_phase);
+          tc_fence_after();
+          issue_s(0, k_slot);
+          umma_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_slot, j == 0);
+        umma_commit(&o_done[1]);
+        umma_commit(&kv_empty[v_slot]);
+        if (has_next) {
+          issue_s(1, k_slot);
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[k_slot]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int t = warp >> 2;     // query tile
+    const int quad = warp & 3;   // TMEM lane quadrant
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + t * 128;
+    const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
+    const float sl2 = p.scale_log2;
+    float m = -INFINITY;  // running max of s * scale_log2 actually used for P
+    float l = 0.f;        // running sum of P
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      const int valid = p.Sk - j * BKV;  // >= 128 except possibly for the last tile
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(s_addr + c * 32, r);
+        tmem_ld_wait();
+        if (valid >= BKV) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c * 32 + k < valid) mx = fmaxf(mx, __uint_as_float(r[k]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * sl2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = (m_new - m) > RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = fast_exp2(m - m_new);
+          l *= alpha;
+          m = m_new;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_x32(o_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+            tmem_st_x32(o_addr + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: P = exp2(s * scale_log2 - m) -> bf16 pairs, written over the first 64 columns of S
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(s_addr + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float e = fast_exp2(__uint_as_float(r[k]) * sl2 - m);
+          if (valid < BKV && c * 32 + k >= valid) e = 0.f;
+          pv[k] = e;
+          lsum += e;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
+        // chunk c of S (fp32 columns [32c, 32c+32)) becomes P columns [16c, 16c+16): always inside the
+        // part of S this thread has already consumed.
+        tmem_st_x16(s_addr + c * 16, pk);
+      }
+      l += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int row = q_block * (2 * BQ) + t * BQ + quad * 32 + lane;
+    __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(o_addr + c * 32, r);
+      tmem_ld_wait();
+      if (row < p.Sq) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
+          reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace attn
+}  // namespace b200
+
+extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                             int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                             int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                             float scale, void* stream) {
+  using namespace b200;
+  using namespace b200::attn;
+  if (!q || !k || !v || !o) return B200_ERR_ARG;
+  if (D != 128) return B200_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return B200_ERR_SHAPE;
+  if (H > 65535 || B > 65535) return B200_ERR_SHAPE;
+  if ((o_sb % 8) || (o_sh % 8) || (o_ss % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return B200_ERR_ALIGN;
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[4] = {64, 128, 1, 1};
+  {
+    uint64_t dims[4] = {128, (uint64_t)Sq, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {1, (uint64_t)q_ss, (uint64_t)q_sh, (uint64_t)q_sb};
+    int rc = make_tmap_bf16(&tmQ, q, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {1, (uint64_t)k_ss, (uint64_t)k_sh, (uint64_t)k_sb};
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {1, (uint64_t)v_ss, (uint64_t)v_sh, (uint64_t)v_sb};
+    int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  Params p;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_sb = o_sb; p.o_sh = o_sh; p.o_ss = o_ss;
+  p.scale_log2 = scale * 1.4426950408889634f;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return B200_ERR_LAUNCH;
+    attr_done = true;
+  }
+  dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}

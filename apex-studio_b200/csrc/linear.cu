@@ -1,0 +1,333 @@
+// b200_linear: C = epilogue(A @ W^T + bias) on the 5th-gen tensor cores.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer   (A tile 128x64, W tile 256x64, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128 N=256 K=16, fp32 accumulators in TMEM,
+//                               two accumulator buffers = all 512 TMEM columns, so the epilogue of tile i
+//                               overlaps the main loop of tile i+1)
+//   warps 2-5   epilogue       (tcgen05.ld 32x32b, bias / gelu-tanh / gate*acc+residual, 16-byte stores)
+// Tiles are walked in groups of GROUP_M row-tiles so that the W panel of a group stays in L2.
+//
+// Reference call sites this replaces: transformer/wan/base/attention.py:345-347,407 (to_q/to_k/to_v/to_out),
+// diffusers FeedForward built at transformer/wan/base/model.py:1062 and called :1270, and the gate/residual
+// updates at model.py:1212-1213,1245-1251,1278-1279 (fused into the epilogue of the preceding projection).
+#include "host_util.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+namespace linear {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int GROUP_M = 16;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  int M, N, K;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* gate;
+  void* C;
+  int64_t ldc;
+  int epi;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  -- torch F.gelu(approximate="tanh")
+  const float k0 = 0.7978845608028654f;
+  const float k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + fast_tanh(inner));
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = GROUP_M * tiles_n;
+  const int group = tile / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int r = tile - group * per_group;
+  tm = first_m + r % gsz;
+  tn = r / gsz;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;   // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full[stage], kb * BK, tm * BM);
+          tma_load_2d(sb, &tmB, &full[stage], kb * BK, tn * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps (2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int tm, tn;
+      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = tm * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tn * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 b = __ldg(bp + q4);
+              v[q4 * 8 + 0] += bf16_lo(b.x); v[q4 * 8 + 1] += bf16_hi(b.x);
+              v[q4 * 8 + 2] += bf16_lo(b.y); v[q4 * 8 + 3] += bf16_hi(b.y);
+              v[q4 * 8 + 4] += bf16_lo(b.z); v[q4 * 8 + 5] += bf16_hi(b.z);
+              v[q4 * 8 + 6] += bf16_lo(b.w); v[q4 * 8 + 7] += bf16_hi(b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+          }
+        }
+        if (p.epi == B200_EPI_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        }
+        if (p.epi == B200_EPI_BIAS_F32) {
+          if (row_ok) {
+            float* cp = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4)
+                reinterpret_cast<float4*>(cp)[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = v[j];
+            }
+          }
+        } else {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col0;
+          if (p.epi == B200_EPI_GATE_RES) {
+            // residual stream update: h = h + gate * (acc + bias), fp32, one rounding.
+            if (row_ok) {
+              if (full_chunk) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  uint4 h = reinterpret_cast<const uint4*>(cp)[q4];
+                  float g[8];
+                  if (p.gate != nullptr) {
+                    uint4 gg = __ldg(reinterpret_cast<const uint4*>(p.gate + col0) + q4);
+                    g[0] = bf16_lo(gg.x); g[1] = bf16_hi(gg.x); g[2] = bf16_lo(gg.y); g[3] = bf16_hi(gg.y);
+                    g[4] = bf16_lo(gg.z); g[5] = bf16_hi(gg.z); g[6] = bf16_lo(gg.w); g[7] = bf16_hi(gg.w);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = 1.0f;
+                  }
+                  float* vv = v + q4 * 8;
+                  uint4 o;
+                  o.x = pack_bf16x2(bf16_lo(h.x) + g[0] * vv[0], bf16_hi(h.x) + g[1] * vv[1]);
+                  o.y = pack_bf16x2(bf16_lo(h.y) + g[2] * vv[2], bf16_hi(h.y) + g[3] * vv[3]);
+                  o.z = pack_bf16x2(bf16_lo(h.z) + g[4] * vv[4], bf16_hi(h.z) + g[5] * vv[5]);
+                  o.w = pack_bf16x2(bf16_lo(h.w) + g[6] * vv[6], bf16_hi(h.w) + g[7] * vv[7]);
+                  reinterpret_cast<uint4*>(cp)[q4] = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) {
+                    float g = p.gate ? __bfloat162float(p.gate[col0 + j]) : 1.0f;
+                    cp[j] = __float2bfloat16(__bfloat162float(cp[j]) + g * v[j]);
+                  }
+              }
+            }
+          } else if (row_ok) {
+            if (full_chunk) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float* vv = v + q4 * 8;
+                uint4 o;
+                o.x = pack_bf16x2(vv[0], vv[1]);
+                o.y = pack_bf16x2(vv[2], vv[3]);
+                o.z = pack_bf16x2(vv[4], vv[5]);
+                o.w = pack_bf16x2(vv[6], vv[7]);
+                reinterpret_cast<uint4*>(cp)[q4] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) cp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace linear
+}  // namespace b200
+
+extern "C" int b200_linear(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N,
+                           int K, int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream) {
+  using namespace b200;
+  using namespace b200::linear;
+  if (!A || !W || !C) return B200_ERR_ARG;
+  if (epilogue < 0 || epilogue > 3) return B200_ERR_ARG;
+  if (M <= 0 || N <= 0 || K <= 0) return B200_ERR_SHAPE;
+  if ((K % 8) || (lda % 8) || (ldw % 8)) return B200_ERR_ALIGN;
+  if (epilogue == B200_EPI_BIAS_F32 ? (ldc % 4) : (ldc % 8)) return B200_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(C) & 15) return B200_ERR_ALIGN;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return B200_ERR_ALIGN;
+  if (gate && (reinterpret_cast<uintptr_t>(gate) & 15)) return B200_ERR_ALIGN;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[2] = {1, (uint64_t)lda};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[2] = {1, (uint64_t)ldw};
+    uint32_t box[2] = {BK, BN};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
+  p.C = C;
+  p.ldc = ldc;
+  p.epi = epilogue;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + BN - 1) / BN;
+  const int total = p.tiles_m * p.tiles_n;
+  const int grid = total < num_sms() ? total : num_sms();
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return B200_ERR_LAUNCH;
+    attr_done = true;
+  }
+  linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}

@@ -1,0 +1,227 @@
+"""Torch-tensor front end of the C ABI (include/apex_b200.h).
+
+Each function extracts raw device pointers, element strides and the current CUDA stream from torch
+tensors, calls the matching ``b200_*`` entry point of libapex_b200.so and maps error codes to the
+exceptions the reference raises at the same place (``ValueError`` for shape/dtype/stride problems as in
+apps/api/src/attention/functions.py:791-801, ``RuntimeError`` otherwise).  PyTorch is used for device
+memory and streams only; all arithmetic happens in the CUDA kernels.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_GELU_TANH, EPI_GATE_RES, EPI_BIAS_F32 = 0, 1, 2, 3
+
+#: number of kernels launched through this module since import / last reset (bench.py's gpu_launches)
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda_bf16(name: str, t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the b200 path has no CPU fallback), got {t.device}")
+    if t.dtype != torch.bfloat16:
+        raise ValueError(f"{name} must be bfloat16, got {t.dtype}")
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# ---------------------------------------------------------------------------------------------------
+# attention core
+# ---------------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v for q [B,H,Sq,128], k/v [B,H,Sk,128] (any strides with a contiguous last dim).
+
+    Returns [B,H,Sq,128] as a transposed view of a [B,Sq,H,128] buffer -- the layout the caller wants next
+    (reference: attention.py:397-401 immediately does ``.transpose(1, 2).flatten(2, 3)``).
+    """
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _require_cuda_bf16(name, t)
+        if t.dim() != 4:
+            raise ValueError(f"{name} must be [B,H,S,D], got shape {tuple(t.shape)}")
+    B, H, Sq, D = q.shape
+    Bk, Hk, Sk, Dk = k.shape
+    if v.shape != k.shape or Bk != B or Hk != H or Dk != D:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}")
+    if D != 128:
+        raise ValueError(f"b200 attention supports head_dim 128 only, got {D}")
+
+    def norm(t):
+        # TMA needs a contiguous last dim and 16-byte aligned strides / base.
+        if t.stride(3) != 1 or any(s % 8 for s in t.stride()[:3]) or t.data_ptr() % 16:
+            return t.contiguous()
+        return t
+
+    q, k, v = norm(q), norm(k), norm(v)
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device).transpose(1, 2)
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lib = _lib.load()
+    rc = lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Sk, D,
+                           q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                           v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
+                           scale, _stream())
+    _lib.check(rc, "b200_attn_fwd")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# linear with fused epilogue
+# ---------------------------------------------------------------------------------------------------
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
+           out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = epilogue(x @ weight^T + bias).  x [..., K] (last dim contiguous), weight [N, K].
+
+    EPI_GATE_RES: ``out`` is the residual stream, updated in place: out += gate * (x @ W^T + bias).
+    """
+    _require_cuda_bf16("x", x)
+    _require_cuda_bf16("weight", weight)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != K:
+        raise ValueError(f"weight {tuple(weight.shape)} does not match x [..., {K}]")
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    if weight.stride(1) != 1:
+        weight = weight.contiguous()
+    M = x2.shape[0]
+    if epilogue == EPI_GATE_RES:
+        if out is None:
+            raise ValueError("EPI_GATE_RES updates `out` (the residual stream) in place; pass it")
+        _require_cuda_bf16("out", out)
+    if out is None:
+        dt = torch.float32 if epilogue == EPI_BIAS_F32 else torch.bfloat16
+        out = torch.empty(x.shape[:-1] + (N,), dtype=dt, device=x.device)
+    o2 = out.view(-1, N) if out.is_contiguous() else out.reshape(-1, N)
+    if o2.data_ptr() != out.data_ptr() or o2.stride(1) != 1:
+        raise ValueError("`out` must be viewable as [M, N] with a contiguous last dim")
+    if o2.shape[0] != M:
+        raise ValueError(f"out rows {o2.shape[0]} != x rows {M}")
+    if bias is not None:
+        _require_cuda_bf16("bias", bias)
+    if gate is not None:
+        _require_cuda_bf16("gate", gate)
+        gate = gate.reshape(-1)
+        if gate.numel() != N or gate.stride(0) != 1:
+            raise ValueError(f"gate must be a contiguous [{N}] vector")
+    lib = _lib.load()
+    rc = lib.b200_linear(x2.data_ptr(), weight.data_ptr(), _ptr(bias), o2.data_ptr(), _ptr(gate), M, N, K,
+                         x2.stride(0), weight.stride(0), o2.stride(0), epilogue, _stream())
+    _lib.check(rc, "b200_linear")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# row kernels
+# ---------------------------------------------------------------------------------------------------
+def layernorm_modulate(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+                       *, ln_weight: Optional[torch.Tensor] = None, ln_bias: Optional[torch.Tensor] = None,
+                       eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FP32LayerNorm(x) [* w + b] [* (1 + scale) + shift]; x [..., dim]; scale/shift [dim] or per-row [rows, dim]."""
+    _require_cuda_bf16("x", x)
+    dim = x.shape[-1]
+    x2 = x.reshape(-1, dim)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    o2 = out.view(-1, dim)
+    mod_stride = 0
+    if scale is not None:
+        _require_cuda_bf16("scale", scale)
+        _require_cuda_bf16("shift", shift)
+        if scale.numel() == dim:
+            scale, shift = scale.reshape(dim).contiguous(), shift.reshape(dim).contiguous()
+        elif scale.numel() == rows * dim:
+            scale, shift = scale.reshape(rows, dim).contiguous(), shift.reshape(rows, dim).contiguous()
+            mod_stride = dim
+        else:
+            raise ValueError(f"scale/shift must have {dim} or {rows * dim} elements, got {scale.numel()}")
+    for name, t in (("ln_weight", ln_weight), ("ln_bias", ln_bias)):
+        if t is not None:
+            _require_cuda_bf16(name, t)
+    lib = _lib.load()
+    rc = lib.b200_layernorm_modulate(x2.data_ptr(), o2.data_ptr(), _ptr(scale), _ptr(shift), _ptr(ln_weight),
+                                     _ptr(ln_bias), rows, dim, x2.stride(0), o2.stride(0), mod_stride, float(eps),
+                                     _stream())
+    _lib.check(rc, "b200_layernorm_modulate")
+    _count()
+    return out
+
+
+def rmsnorm_rope_(x: torch.Tensor, weight: Optional[torch.Tensor], rope: Optional[torch.Tensor], heads: int,
+                  eps: float = 1e-6, *, norm: bool = True) -> torch.Tensor:
+    """In place: x <- RoPE(RMSNorm_over_all_channels(x) * weight).  x [rows, heads*head_dim] (row stride free).
+
+    rope: bf16 [rows, head_dim] interleaved (cos0, sin0, cos1, sin1, ...) or None.
+    """
+    _require_cuda_bf16("x", x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [rows, dim] with a contiguous last dim")
+    rows, dim = x.shape
+    if dim % heads:
+        raise ValueError(f"dim {dim} not divisible by heads {heads}")
+    head_dim = dim // heads
+    if weight is not None:
+        _require_cuda_bf16("weight", weight)
+    if rope is not None:
+        _require_cuda_bf16("rope", rope)
+        if tuple(rope.shape) != (rows, head_dim) or not rope.is_contiguous():
+            raise ValueError(f"rope must be contiguous [{rows}, {head_dim}], got {tuple(rope.shape)}")
+    lib = _lib.load()
+    rc = lib.b200_rmsnorm_rope(x.data_ptr(), _ptr(weight), _ptr(rope), rows, heads, head_dim, x.stride(0),
+                               float(eps) if norm else -1.0, _stream())
+    _lib.check(rc, "b200_rmsnorm_rope")
+    _count()
+    return x
+
+
+def gate_residual_(h: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place: h += y * gate (gate [dim] or None)."""
+    _require_cuda_bf16("h", h)
+    _require_cuda_bf16("y", y)
+    dim = h.shape[-1]
+    h2, y2 = h.view(-1, dim), y.reshape(-1, dim)
+    if gate is not None:
+        _require_cuda_bf16("gate", gate)
+        gate = gate.reshape(dim).contiguous()
+    lib = _lib.load()
+    rc = lib.b200_gate_residual(h2.data_ptr(), y2.data_ptr(), _ptr(gate), h2.shape[0], dim, h2.stride(0),
+                                y2.stride(0), _stream())
+    _lib.check(rc, "b200_gate_residual")
+    _count()
+    return h
+
+
+def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance_scale: float) -> torch.Tensor:
+    """float32( uncond + g * (cond - uncond) ) with the reference's bf16 rounding (wan/shared/__init__.py:565)."""
+    _require_cuda_bf16("cond", cond)
+    _require_cuda_bf16("uncond", uncond)
+    cond, uncond = cond.contiguous(), uncond.contiguous()
+    out = torch.empty(cond.shape, dtype=torch.float32, device=cond.device)
+    lib = _lib.load()
+    rc = lib.b200_cfg_combine(cond.data_ptr(), uncond.data_ptr(), out.data_ptr(), float(guidance_scale),
+                              cond.numel(), _stream())
+    _lib.check(rc, "b200_cfg_combine")
+    _count()
+    return out

@@ -1,0 +1,9 @@
+"""Import shim: the package lives in ``apex-studio_b200/`` (the repository's required directory name,
+which is not a valid Python identifier); this module makes it importable as ``apex_studio_b200``."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "apex-studio_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _os, _f

@@ -1,0 +1,112 @@
+/*
+ * apex_b200.h -- C ABI of libapex_b200.so, the sm_100a (B200) implementation of the denoising hot path of
+ * Apex Studio's generation server (reference: totokunda/apex-studio, apps/api).
+ *
+ * The reference has no native ABI on this path: it is Python calling torch.  Each entry point below
+ * replaces one Python-level call site of the reference (cited as file:line under apps/api/src/), taking
+ * what that call site holds at that moment -- device pointers, shapes, element strides, scalars -- plus
+ * the CUDA stream to launch on.  No torch types, no allocation inside, no global state besides lazily
+ * resolved driver entry points.  Every function returns 0 (B200_OK) or a negative error code and never
+ * throws; the Python shim (apex-studio_b200/ops.py) turns codes into the exceptions the reference raises
+ * (ValueError for shape/dtype/alignment problems, RuntimeError otherwise).
+ *
+ * All tensors are bf16 unless stated otherwise; "stride" arguments are in ELEMENTS.
+ * `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef APEX_B200_H_
+#define APEX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_SHAPE (-1)  /* unsupported shape (e.g. head_dim != 128)            -> ValueError   */
+#define B200_ERR_ALIGN (-2)  /* pointer/stride not 16-byte aligned                   -> ValueError   */
+#define B200_ERR_DRIVER (-3) /* CUDA driver entry point unavailable (no GPU/driver)  -> RuntimeError */
+#define B200_ERR_TMAP (-4)   /* cuTensorMapEncodeTiled rejected the layout           -> RuntimeError */
+#define B200_ERR_LAUNCH (-5) /* kernel launch failed                                 -> RuntimeError */
+#define B200_ERR_ARG (-6)    /* null pointer / bad enum                              -> ValueError   */
+
+/* Library / ABI version (major*100+minor). */
+int b200_version(void);
+
+/* Human-readable message for an error code (static storage). */
+const char* b200_strerror(int code);
+
+/*
+ * Attention core: o = softmax(q k^T * scale) v, non-causal, no mask, no dropout.
+ * Replaces attention_register.call(q, k, v, ...) -- attention/functions.py:84,338-377 (`sdpa` is the gold
+ * backend), called from transformer/wan/base/attention.py:397 (self and cross attention) and from every
+ * other DiT family (flux/base/attention.py:89, qwenimage/base/attention.py:138, hunyuanvideo15/base/model.py:150).
+ *   q: [B,H,Sq,D]  k,v: [B,H,Sk,D]  o: [B,H,Sq,D]   D must be 128; last dim contiguous; every other stride
+ *   arbitrary but a multiple of 8 elements (16 bytes).  fp32 softmax / accumulation, P rounded to bf16
+ *   before P*V (as flash kernels do).
+ */
+int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                  int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                  int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                  float scale, void* stream);
+
+/*
+ * Linear layer with fused epilogue: C = epilogue(A @ W^T + bias).
+ *   A: [M,K] row stride lda;  W: [N,K] row stride ldw (nn.Linear weight layout);  bias: [N] or NULL.
+ * epilogue:
+ *   B200_EPI_BIAS      C[M,N] (ldc) = acc + bias                         attention.py:345-347,407 (to_q/k/v, to_out)
+ *   B200_EPI_GELU_TANH C = gelu_tanh(acc + bias)                         diffusers FeedForward("gelu-approximate"), model.py:1062,1270
+ *   B200_EPI_GATE_RES  C (read-modify-write, the residual stream) += gate[n] * (acc + bias); gate NULL => 1
+ *                                                                        model.py:1212-1213, 1245-1251, 1278-1279
+ *   B200_EPI_BIAS_F32  C is float32 [M,N] (ldc in float elements) = acc + bias (output head / embedders)
+ * K must be a multiple of 8; lda, ldw multiples of 8; ldc multiple of 8 (bf16) / 4 (f32); pointers 16 B aligned.
+ */
+#define B200_EPI_BIAS 0
+#define B200_EPI_GELU_TANH 1
+#define B200_EPI_GATE_RES 2
+#define B200_EPI_BIAS_F32 3
+int b200_linear(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N, int K,
+                int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream);
+
+/*
+ * y = LayerNorm_fp32(x, eps, no affine) * (1 + scale) + shift      (adaLN modulate)
+ * Replaces _chunked_modulated_norm -- transformer/wan/base/model.py:56-116 with apply_scale_shift_inplace
+ * (transformer/efficiency/ops.py:37-56).  x,y: [rows, dim] (row strides ldx, ldy); scale, shift: [dim] bf16
+ * shared by all rows (mod_stride = 0) or per-row [rows, dim] with row stride mod_stride (Wan 2.2 5B ti2v).
+ * With scale == NULL it is the plain FP32LayerNorm with optional affine weight/bias (norm2, model.py:1219;
+ * ln_w, ln_b: [dim] fp32-or-bf16 given as bf16 here) or no affine at all.
+ */
+int b200_layernorm_modulate(const void* x, void* y, const void* scale, const void* shift, const void* ln_w,
+                            const void* ln_b, int rows, int dim, int64_t ldx, int64_t ldy, int64_t mod_stride,
+                            float eps, void* stream);
+
+/*
+ * In-place q/k RMS-norm over the full channel dim (across heads) followed by Wan 3-axis RoPE on
+ * (even, odd) pairs.  Replaces InplaceRMSNorm.forward (transformer/efficiency/mod.py:24-35) +
+ * apply_wan_rope_inplace (transformer/efficiency/ops.py:101-160) at attention.py:349-370.
+ *   x: [rows, heads*head_dim] row stride ldx, modified in place; w: [heads*head_dim] bf16 norm weight or NULL;
+ *   rope: float32 [rows, head_dim/2, 2] (cos, sin) shared by all heads, or NULL for no RoPE (cross-attn q/k).
+ * The reference's bf16 rounding points are reproduced (rsqrt factor, weight multiply, cos/sin cast to bf16,
+ * mul_ then addcmul_).
+ */
+int b200_rmsnorm_rope(void* x, const void* w, const void* rope, int rows, int heads, int head_dim, int64_t ldx,
+                      float eps, void* stream);
+
+/*
+ * h += y * gate   (apply_gate_inplace + add_, transformer/efficiency/ops.py:19-34, model.py:1212-1213).
+ * gate: [dim] bf16 or NULL (plain residual add, model.py:1245-1251).  Stand-alone form of B200_EPI_GATE_RES
+ * for callers whose y comes from somewhere else.
+ */
+int b200_gate_residual(void* h, const void* y, const void* gate, int rows, int dim, int64_t ldh, int64_t ldy,
+                       void* stream);
+
+/*
+ * Classifier-free-guidance combine + fp32 promotion: out_f32 = u + g * (c - u) computed as the reference
+ * does in bf16 (engine/wan/shared/__init__.py:565) then widened to fp32 for the scheduler (scheduler/unipc.py:317).
+ */
+int b200_cfg_combine(const void* cond, const void* uncond, float* out_f32, float guidance, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APEX_B200_H_ */
