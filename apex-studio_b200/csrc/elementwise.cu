@@ -222,19 +222,19 @@ gate_residual_kernel(__nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// noise = u + g * (c - u) in bf16 tensor arithmetic (three roundings), widened to fp32.
+// noise = u + g * (c - u) in bf16 tensor arithmetic (three roundings), bf16 out like the reference.
 // reference: engine/wan/shared/__init__.py:565
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-cfg_combine_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ u, float* __restrict__ out,
-                   float g, int64_t n) {
+cfg_combine_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ u,
+                   __nv_bfloat16* __restrict__ out, float g, int64_t n) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float cf = __bfloat162float(c[i]);
     const float uf = __bfloat162float(u[i]);
     const float d = round_bf16(cf - uf);
     const float gd = round_bf16(g * d);
-    out[i] = round_bf16(uf + gd);
+    out[i] = __float2bfloat16(uf + gd);
   }
 }
 
@@ -313,15 +313,15 @@ extern "C" int b200_gate_residual(void* h, const void* y, const void* gate, int 
   return B200_OK;
 }
 
-extern "C" int b200_cfg_combine(const void* cond, const void* uncond, float* out_f32, float guidance, int64_t n,
+extern "C" int b200_cfg_combine(const void* cond, const void* uncond, void* out, float guidance, int64_t n,
                                 void* stream) {
-  if (!cond || !uncond || !out_f32) return B200_ERR_ARG;
+  if (!cond || !uncond || !out) return B200_ERR_ARG;
   if (n <= 0) return B200_ERR_SHAPE;
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   cfg_combine_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __nv_bfloat16*)cond, (const __nv_bfloat16*)uncond, out_f32, guidance, n);
+      (const __nv_bfloat16*)cond, (const __nv_bfloat16*)uncond, (__nv_bfloat16*)out, guidance, n);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

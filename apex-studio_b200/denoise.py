@@ -1,0 +1,102 @@
+"""Wan denoise loops on the B200 backend.
+
+Mirrors ``WanShared.moe_denoise`` / ``base_denoise`` (apps/api/src/engine/wan/shared/__init__.py:478-608,
+:610-755) with the same keyword names: per step pick the expert by ``t >= boundary_timestep`` (:335-337,
+both experts stay resident in the 180 GB of HBM instead of the reference's offload swap :341-462), pick the
+guidance scale the same way (:464-476), run the conditional and the unconditional forward on
+``latents.to(transformer_dtype)`` (:521), combine ``u + g * (c - u)`` in bf16 (:565), and advance the fp32
+latents with ``scheduler.step`` (:569).
+
+Multi-GPU (``parallel.ParallelContext``): the two CFG branches are independent given the same latents, so
+with a CFG group of 2 each rank runs ONE branch and the branches are exchanged with a single all-gather of
+the [B,16,F,H,W] bf16 prediction per step; every rank then takes the identical (deterministic, fp32)
+scheduler step, so latents never need a broadcast.  Inside a forward the token axis may additionally be
+sharded over a sequence-parallel group (wan/model.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Union
+
+import torch
+
+from . import ops
+from .parallel import ParallelContext
+
+
+@dataclass
+class DenoiseTrace:
+    """Integer decisions of a run -- compared with ``==`` against the oracle / reference in the tests."""
+    timesteps: List[int] = field(default_factory=list)
+    expert: List[str] = field(default_factory=list)          # "high" | "low" per step
+    guidance: List[float] = field(default_factory=list)
+
+
+def select_expert_is_high(t: Union[torch.Tensor, int, float], boundary_timestep) -> bool:
+    """engine/wan/shared/__init__.py:335-337."""
+    return boundary_timestep is not None and bool(t >= boundary_timestep)
+
+
+def select_guidance_scale(t, boundary_timestep, guidance_scale: Union[float, Sequence[float]]) -> float:
+    """engine/wan/shared/__init__.py:464-476."""
+    if isinstance(guidance_scale, (list, tuple)):
+        return float(guidance_scale[0] if select_expert_is_high(t, boundary_timestep) else guidance_scale[1])
+    return float(guidance_scale)
+
+
+@torch.inference_mode()
+def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, high_noise_transformer,
+                low_noise_transformer=None, boundary_timestep=None, guidance_scale: Union[float, Sequence[float]] = 5.0,
+                transformer_kwargs: Optional[Dict[str, Any]] = None,
+                unconditional_transformer_kwargs: Optional[Dict[str, Any]] = None, use_cfg_guidance: bool = True,
+                transformer_dtype=torch.bfloat16, extra_step_kwargs: Optional[Dict[str, Any]] = None,
+                denoise_progress_callback: Optional[Callable] = None, parallel: Optional[ParallelContext] = None,
+                trace: Optional[DenoiseTrace] = None) -> torch.Tensor:
+    """Returns the final fp32 latents.  ``low_noise_transformer=None`` gives ``base_denoise`` (single expert)."""
+    transformer_kwargs = dict(transformer_kwargs or {})
+    uncond_kwargs = dict(unconditional_transformer_kwargs or {})
+    transformer_kwargs.pop("encoder_hidden_states_image", None)
+    uncond_kwargs.pop("encoder_hidden_states_image", None)
+    extra_step_kwargs = extra_step_kwargs or {}
+    do_cfg = bool(use_cfg_guidance and uncond_kwargs)
+    par = parallel or ParallelContext.single()
+    total = len(timesteps)
+    for i, t in enumerate(timesteps):
+        latent_model_input = latents.to(transformer_dtype)
+        timestep = t.expand(latents.shape[0])
+        high = select_expert_is_high(t, boundary_timestep)
+        transformer = high_noise_transformer if (high or low_noise_transformer is None) else low_noise_transformer
+        g = select_guidance_scale(t, boundary_timestep, guidance_scale)
+        if trace is not None:
+            trace.timesteps.append(int(t))
+            trace.expert.append("high" if (high or low_noise_transformer is None) else "low")
+            trace.guidance.append(g)
+
+        if do_cfg and par.cfg_size == 2:
+            # one branch per CFG rank, one all-gather of the predictions
+            kw = transformer_kwargs if par.cfg_rank == 0 else uncond_kwargs
+            mine = transformer(hidden_states=latent_model_input, timestep=timestep, return_dict=False,
+                               parallel=par, **kw)[0]
+            cond, uncond = par.exchange_cfg(mine)
+            noise_pred = ops.cfg_combine(cond, uncond, g)
+        else:
+            cond = transformer(hidden_states=latent_model_input, timestep=timestep, return_dict=False,
+                               parallel=par, **transformer_kwargs)[0]
+            if do_cfg:
+                uncond = transformer(hidden_states=latent_model_input, timestep=timestep, return_dict=False,
+                                     parallel=par, **uncond_kwargs)[0]
+                noise_pred = ops.cfg_combine(cond, uncond, g)
+            else:
+                noise_pred = cond
+        latents = scheduler.step(noise_pred, t, latents, **extra_step_kwargs, return_dict=False)[0]
+        if denoise_progress_callback is not None:
+            denoise_progress_callback(float(i + 1) / float(total), f"Denoising step {i + 1}/{total}")
+    return latents
+
+
+def base_denoise(**kwargs) -> torch.Tensor:
+    """Single-expert loop (engine/wan/shared/__init__.py:610-755): ``transformer=`` instead of the expert pair."""
+    transformer = kwargs.pop("transformer")
+    kwargs.pop("low_noise_transformer", None)
+    kwargs["boundary_timestep"] = None
+    return moe_denoise(high_noise_transformer=transformer, low_noise_transformer=None, **kwargs)

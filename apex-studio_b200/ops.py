@@ -214,11 +214,11 @@ def gate_residual_(h: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor
 
 
 def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance_scale: float) -> torch.Tensor:
-    """float32( uncond + g * (cond - uncond) ) with the reference's bf16 rounding (wan/shared/__init__.py:565)."""
+    """uncond + g * (cond - uncond) with the reference's bf16 rounding, bf16 out (wan/shared/__init__.py:565)."""
     _require_cuda_bf16("cond", cond)
     _require_cuda_bf16("uncond", uncond)
     cond, uncond = cond.contiguous(), uncond.contiguous()
-    out = torch.empty(cond.shape, dtype=torch.float32, device=cond.device)
+    out = torch.empty(cond.shape, dtype=torch.bfloat16, device=cond.device)
     lib = _lib.load()
     rc = lib.b200_cfg_combine(cond.data_ptr(), uncond.data_ptr(), out.data_ptr(), float(guidance_scale),
                               cond.numel(), _stream())

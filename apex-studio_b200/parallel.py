@@ -1,0 +1,170 @@
+"""One-process-per-GPU sharding of the denoise step over the NVLink/NVSwitch domain of one box.
+
+The reference has no live multi-GPU path for one job (one Ray actor per device, whole
+jobs only); this module introduces the partitioning the north star asks for, in the two places where the
+path really shards:
+
+* **CFG pair** -- the conditional and unconditional forwards of a step (engine/wan/shared/__init__.py:548-563)
+  are independent given the same latents: ranks are laid out as ``cfg_size x sp_size`` (cfg-major), branch
+  ``cfg_rank`` runs on its ``sp_size`` ranks, and the two [B,16,F,H,W] bf16 predictions are exchanged with ONE
+  all-gather per step inside the pair {r, r + sp_size}.
+* **token shards** -- inside a forward everything except the self-attention core is token-independent, so the
+  token axis is split into ``sp_size`` contiguous shards; around the global self-attention the shards are
+  re-partitioned from tokens to heads and back (Ulysses): all-to-all #1 sends each rank the q|k|v columns of
+  its ``heads / sp_size`` heads for all tokens, all-to-all #2 returns the attention output to token shards.
+  Results are identical to the unsharded forward (no windowing / approximation).
+* **decoded frames** -- VAE spatial tiles are dealt round-robin over all ranks and reassembled with a single
+  all-gather (``allgather_frames``).
+
+Plumbing is ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); all timing of multi-GPU runs is done
+on the device by the caller.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ParallelContext:
+    rank: int = 0
+    world_size: int = 1
+    cfg_size: int = 1
+    sp_size: int = 1
+    cfg_group: Optional[object] = None   # process group of my CFG pair
+    sp_group: Optional[object] = None    # process group of my token-shard peers
+    world_group: Optional[object] = None
+
+    # ------------------------------------------------------------------------------------ construction
+    @classmethod
+    def single(cls) -> "ParallelContext":
+        return cls()
+
+    @classmethod
+    def create(cls, use_cfg: bool = True, world_group=None) -> "ParallelContext":
+        """Build the cfg x sp layout for the initialised default process group.  Every rank must call this
+        (``dist.new_group`` is collective)."""
+        if not dist.is_available() or not dist.is_initialized():
+            return cls.single()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        cfg_size, sp_size = plan_layout(world, use_cfg)
+        cfg_group = sp_group = None
+        # sp groups: contiguous blocks of sp_size ranks; cfg groups: {r, r + sp_size}
+        for c in range(cfg_size):
+            ranks = list(range(c * sp_size, (c + 1) * sp_size))
+            g = dist.new_group(ranks)
+            if rank in ranks:
+                sp_group = g
+        for s in range(sp_size):
+            ranks = [s + c * sp_size for c in range(cfg_size)]
+            g = dist.new_group(ranks)
+            if rank in ranks:
+                cfg_group = g
+        return cls(rank=rank, world_size=world, cfg_size=cfg_size, sp_size=sp_size, cfg_group=cfg_group,
+                   sp_group=sp_group, world_group=world_group)
+
+    @property
+    def cfg_rank(self) -> int:
+        return self.rank // self.sp_size
+
+    @property
+    def sp_rank(self) -> int:
+        return self.rank % self.sp_size
+
+    # ------------------------------------------------------------------------------------ CFG exchange
+    def exchange_cfg(self, mine: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """All-gather the branch predictions inside the CFG pair; returns (cond, uncond)."""
+        if self.cfg_size == 1:
+            raise RuntimeError("exchange_cfg needs cfg_size == 2")
+        mine = mine.contiguous()
+        both = torch.empty((2,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(both, mine, group=self.cfg_group)
+        return both[0], both[1]
+
+    # ------------------------------------------------------------------------------------ token shards
+    def shard_bounds(self, tokens: int) -> Tuple[int, int]:
+        if tokens % self.sp_size:
+            raise ValueError(f"token count {tokens} is not divisible by the sequence-parallel size {self.sp_size}")
+        n = tokens // self.sp_size
+        return self.sp_rank * n, (self.sp_rank + 1) * n
+
+    def tokens_to_heads(self, qkv_local: torch.Tensor, heads: int, head_dim: int) -> torch.Tensor:
+        """[S/P, 3*H*Dh] (q|k|v column blocks of my tokens) -> [3, S, (H/P)*Dh] (all tokens, my heads).
+
+        Pack so that destination r's data is contiguous -- [P, 3, S/P, (H/P)*Dh] -- then one all_to_all_single;
+        the receive buffer [P(src), 3, S/P, hp*Dh] is permuted to [3, P*S/P = S, hp*Dh] (source-rank order is
+        token order because shards are contiguous)."""
+        P = self.sp_size
+        n_local = qkv_local.shape[0]
+        hp = heads // P
+        if heads % P:
+            raise ValueError(f"{heads} heads are not divisible by the sequence-parallel size {P}")
+        send = qkv_local.view(n_local, 3, P, hp * head_dim).permute(2, 1, 0, 3).contiguous()
+        recv = torch.empty_like(send)
+        all_to_all_single(recv, send, self.sp_group)
+        return recv.permute(1, 0, 2, 3).reshape(3, P * n_local, hp * head_dim)
+
+    def heads_to_tokens(self, o_heads: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[S, (H/P)*Dh] (all tokens, my heads) -> [S/P, H*Dh] (my tokens, all heads)."""
+        P = self.sp_size
+        S, w = o_heads.shape
+        n_local = S // P
+        send = o_heads.contiguous()                      # chunk r = tokens of rank r, already contiguous
+        recv = torch.empty_like(send)                    # [P(src = head group), S/P, hp*Dh]
+        all_to_all_single(recv, send, self.sp_group)
+        res = recv.view(P, n_local, w).permute(1, 0, 2).reshape(n_local, P * w)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res.contiguous()
+
+    def gather_tokens(self, local: torch.Tensor) -> torch.Tensor:
+        """[S/P, C] -> [S, C] on every rank of the sp group (used once per forward for the output head)."""
+        if self.sp_size == 1:
+            return local
+        local = local.contiguous()
+        full = torch.empty((self.sp_size * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                           device=local.device)
+        dist.all_gather_into_tensor(full, local, group=self.sp_group)
+        return full
+
+    # ------------------------------------------------------------------------------------ frames
+    def allgather_frames(self, mine: torch.Tensor) -> torch.Tensor:
+        """Single all-gather over ALL ranks of equally shaped per-rank tile stacks -> [world, ...]."""
+        if self.world_size == 1:
+            return mine.unsqueeze(0)
+        mine = mine.contiguous()
+        out = torch.empty((self.world_size,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(out, mine, group=self.world_group)
+        return out
+
+
+def plan_layout(world_size: int, use_cfg: bool) -> Tuple[int, int]:
+    """(cfg_size, sp_size): the CFG pair takes the first factor of 2 when guidance is on."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    cfg = 2 if (use_cfg and world_size % 2 == 0) else 1
+    return cfg, world_size // cfg
+
+
+def all_to_all_single(recv: torch.Tensor, send: torch.Tensor, group) -> None:
+    """dist.all_to_all_single with an all-gather based emulation for backends without it (gloo, CPU tests)."""
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.all_to_all_single(recv, send, group=group)
+        return
+    P = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    parts = [torch.empty_like(send) for _ in range(P)]
+    dist.all_gather(parts, send.contiguous(), group=group)
+    chunk = send.shape[0] // P
+    for src in range(P):
+        recv[src * chunk:(src + 1) * chunk].copy_(parts[src][me * chunk:(me + 1) * chunk])
+
+
+def deal_round_robin(n_items: int, world_size: int, rank: int) -> List[int]:
+    """Indices of the items (VAE tiles) rank ``rank`` owns: i with i % world == rank."""
+    return [i for i in range(n_items) if i % world_size == rank]

@@ -85,7 +85,8 @@ int b200_layernorm_modulate(const void* x, void* y, const void* scale, const voi
  * (even, odd) pairs.  Replaces InplaceRMSNorm.forward (transformer/efficiency/mod.py:24-35) +
  * apply_wan_rope_inplace (transformer/efficiency/ops.py:101-160) at attention.py:349-370.
  *   x: [rows, heads*head_dim] row stride ldx, modified in place; w: [heads*head_dim] bf16 norm weight or NULL;
- *   rope: float32 [rows, head_dim/2, 2] (cos, sin) shared by all heads, or NULL for no RoPE (cross-attn q/k).
+ *   rope: bf16 [rows, head_dim] = (cos0, sin0, cos1, sin1, ...) already cast to bf16 as the reference casts them,
+ *   shared by all heads, or NULL for no RoPE (cross-attn q/k).  eps < 0 skips the norm (RoPE only).
  * The reference's bf16 rounding points are reproduced (rsqrt factor, weight multiply, cos/sin cast to bf16,
  * mul_ then addcmul_).
  */
@@ -101,10 +102,11 @@ int b200_gate_residual(void* h, const void* y, const void* gate, int rows, int d
                        void* stream);
 
 /*
- * Classifier-free-guidance combine + fp32 promotion: out_f32 = u + g * (c - u) computed as the reference
- * does in bf16 (engine/wan/shared/__init__.py:565) then widened to fp32 for the scheduler (scheduler/unipc.py:317).
+ * Classifier-free-guidance combine: out = u + g * (c - u), computed as the reference's bf16 tensor expression
+ * does (three bf16 roundings; engine/wan/shared/__init__.py:565).  out is bf16 like the reference's noise_pred,
+ * which the scheduler then consumes (scheduler/unipc.py:317).
  */
-int b200_cfg_combine(const void* cond, const void* uncond, float* out_f32, float guidance, int64_t n, void* stream);
+int b200_cfg_combine(const void* cond, const void* uncond, void* out, float guidance, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,143 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own modules (imported unmodified from
+/root/reference through oracle/ref_import) on seeded synthetic inputs.  Run in the build container only:
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+The fixtures pin (a) the CPU oracle restatement (tests/test_oracle_golden.py, CPU) and (b) the CUDA path
+(tests/test_gpu_parity.py, GPU) to the reference.  bf16 tensors are stored widened to float32 (exact).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+from ref_import import bootstrap  # noqa: E402
+import wan_dit  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+DIT_CONFIGS = {
+    # name: (model kwargs, latent shape, text len)
+    "dit_s72": (dict(dim=256, heads=2, ffn_dim=512, num_layers=2, text_dim=64, freq_dim=256), (1, 16, 3, 8, 12), 16),
+    "dit_s400": (dict(dim=256, heads=2, ffn_dim=384, num_layers=1, text_dim=64, freq_dim=256), (1, 16, 5, 16, 20), 40),
+}
+
+
+def f32(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def build_reference_dit(cfg, weights):
+    m = bootstrap.ref("src.transformer.wan.base.model")
+    a = bootstrap.ref("src.attention.functions")
+    a.attention_register.set_default("sdpa")
+    model = m.WanTransformer3DModel(
+        num_attention_heads=cfg["heads"], attention_head_dim=cfg["dim"] // cfg["heads"], in_channels=16,
+        out_channels=16, text_dim=cfg["text_dim"], freq_dim=cfg["freq_dim"], ffn_dim=cfg["ffn_dim"],
+        num_layers=cfg["num_layers"])
+    missing, unexpected = model.load_state_dict(weights, strict=False)
+    assert not unexpected, unexpected
+    # only buffers-free modules may be "missing" (none expected)
+    assert not missing, missing
+    return model.eval()
+
+
+def golden_dit():
+    for name, (cfg, lshape, tlen) in DIT_CONFIGS.items():
+        out = {}
+        w32 = wan_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+        g = torch.Generator().manual_seed(42)
+        latents = torch.randn(lshape, generator=g)
+        text = torch.randn(1, tlen, cfg["text_dim"], generator=torch.Generator().manual_seed(43))
+        t = torch.tensor([875], dtype=torch.int64)
+        out["latents"], out["text"], out["timestep"] = f32(latents), f32(text), t.numpy()
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            model = build_reference_dit(cfg, w32).to(dt)
+            with torch.inference_mode():
+                y = model(latents.to(dt), t, text.to(dt), return_dict=False)[0]
+            out["out_" + tag] = f32(y)
+            # intermediate pins: rope table, condition embedder, first block
+            with torch.inference_mode():
+                rot = model.rope.forward_hidden_states(latents)
+                out["rope_real"] = rot.real[0, 0].numpy()
+                out["rope_imag"] = rot.imag[0, 0].numpy()
+                temb, tproj, ctx, _, _ = model.condition_embedder(t, text.to(dt), None, None)
+                out["temb_" + tag], out["tproj_" + tag], out["ctx_" + tag] = f32(temb), f32(tproj), f32(ctx)
+                hs = model.patch_embedding(latents.to(dt)).flatten(2).transpose(1, 2)
+                out["patch_" + tag] = f32(hs)
+                b0 = model.blocks[0](hs.clone(), ctx, tproj.unflatten(1, (6, -1)), rot)
+                out["block0_" + tag] = f32(b0)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
+def golden_attention():
+    """The reference's own differential recipe (scripts/smoke_tests/test_attention_backends.py:232-388):
+    B,H,S,D = 1,32,1024,128, seed 42, q,k,v = randn; gold = attention_register.get('sdpa').  On the CPU the
+    recipe runs in fp32; we keep a 4-head slice of the gold output to stay small."""
+    a = bootstrap.ref("src.attention.functions")
+    torch.manual_seed(42)
+    q = torch.randn(1, 32, 1024, 128)
+    k = torch.randn(1, 32, 1024, 128)
+    v = torch.randn(1, 32, 1024, 128)
+    gold = a.attention_register.get("sdpa")(q, k, v)
+    # cross-attention shaped case (Sq != Sk, ragged)
+    torch.manual_seed(7)
+    q2, k2, v2 = torch.randn(1, 2, 300, 128), torch.randn(1, 2, 77, 128), torch.randn(1, 2, 77, 128)
+    gold2 = a.attention_register.get("sdpa")(q2, k2, v2)
+    np.savez_compressed(os.path.join(GOLDEN, "attention.npz"), heads=np.array([0, 7, 19, 31]),
+                        gold_1x32x1024x128_seed42=f32(gold[:, [0, 7, 19, 31]]),
+                        q2=f32(q2), k2=f32(k2), v2=f32(v2), gold2=f32(gold2))
+    print("attention", gold.shape)
+
+
+def synthetic_model(sample: torch.Tensor, t: int) -> torch.Tensor:
+    """Deterministic stand-in for the DiT inside scheduler goldens (same formula in the tests)."""
+    return 0.35 * sample + 0.1 * torch.sin(sample * 3.0 + float(t) * 0.01)
+
+
+def golden_scheduler():
+    """Run the reference's own UniPCMultistepScheduler (scheduler/unipc.py) for several step counts."""
+    u = bootstrap.ref("src.scheduler.unipc")
+    out = {}
+    for n, shift in ((4, 3.0), (8, 5.0), (50, 3.0), (50, 1.0)):
+        sch = u.UniPCMultistepScheduler(shift=shift)
+        sch.set_timesteps(n)
+        tag = f"n{n}_s{shift:g}"
+        out[tag + "_timesteps"] = sch.timesteps.numpy().astype(np.int64)
+        out[tag + "_sigmas"] = sch.sigmas.numpy().astype(np.float32)
+        x = torch.randn(1, 16, 2, 6, 8, generator=torch.Generator().manual_seed(42))
+        out[tag + "_x0"] = f32(x)
+        trace, norms = [], []
+        for t in sch.timesteps:
+            had_last = sch.last_sample is not None
+            idx_before = sch.step_index
+            mo = synthetic_model(x, int(t))
+            x = sch.step(mo, t, x, return_dict=False)[0]
+            idx = sch.step_index - 1
+            use_corr = idx > 0 and (idx - 1) not in sch.disable_corrector and had_last
+            trace.append((idx, sch.this_order, int(use_corr)))
+            norms.append(float(x.double().norm()))
+        out[tag + "_trace"] = np.array(trace, dtype=np.int64)
+        out[tag + "_norms"] = np.array(norms, dtype=np.float64)
+        out[tag + "_final"] = f32(x)
+    np.savez_compressed(os.path.join(GOLDEN, "unipc.npz"), **out)
+    print("scheduler", sorted(out)[:6], "...")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae"]
+    for wname in which:
+        fn = globals().get("golden_" + wname)
+        if fn is None:
+            print("skip", wname)
+            continue
+        fn()

@@ -1,0 +1,118 @@
+"""Scheduler: integer step indexing bit-exact vs the reference (golden from the reference class itself),
+float update within 2e-6 (oracle, numpy) / exact (product, torch on CPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import unipc
+from apex_studio_b200.denoise import select_expert_is_high, select_guidance_scale
+from apex_studio_b200.scheduler import UniPCMultistepScheduler, get_timesteps
+from conftest import GOLDEN
+
+CASES = [(4, 3.0), (8, 5.0), (50, 3.0), (50, 1.0)]
+
+
+def synthetic_model(sample, t):
+    return 0.35 * sample + 0.1 * torch.sin(sample * 3.0 + float(t) * 0.01)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "unipc.npz"))
+
+
+@pytest.mark.parametrize("n,shift", CASES)
+def test_integer_schedule_bit_exact(gold, n, shift):
+    tag = f"n{n}_s{shift:g}"
+    sig, ts = unipc.make_schedule(n, shift)
+    assert ts.dtype == np.int64 and np.array_equal(ts, gold[tag + "_timesteps"])
+    assert np.array_equal(sig, gold[tag + "_sigmas"])
+    s = UniPCMultistepScheduler(shift=shift)
+    s.set_timesteps(n)
+    assert s.timesteps.dtype == torch.int64 and np.array_equal(s.timesteps.numpy(), gold[tag + "_timesteps"])
+    assert np.array_equal(s.sigmas.numpy(), gold[tag + "_sigmas"])
+    assert np.array_equal(np.array([(a, b, int(c)) for a, b, c in unipc.step_orders(n)]), gold[tag + "_trace"])
+
+
+@pytest.mark.parametrize("n,shift", CASES)
+def test_full_run_vs_reference(gold, n, shift):
+    tag = f"n{n}_s{shift:g}"
+    ref = gold[tag + "_final"]
+    # product scheduler (torch, CPU here / GPU in production)
+    s = UniPCMultistepScheduler(shift=shift)
+    s.set_timesteps(n)
+    x = torch.from_numpy(gold[tag + "_x0"].copy())
+    norms = []
+    for t in s.timesteps:
+        x = s.step(synthetic_model(x, int(t)), t, x)[0]
+        norms.append(float(x.double().norm()))
+    assert np.array_equal(np.array([(a, b, int(c)) for a, b, c in s.trace]), gold[tag + "_trace"])
+    assert np.abs(x.numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.allclose(norms, gold[tag + "_norms"], rtol=2e-6)
+    # numpy oracle
+    sig, ts = unipc.make_schedule(n, shift)
+    o = unipc.UniPCOracle(sig, ts)
+    y = gold[tag + "_x0"].copy()
+    for t in ts:
+        y = o.step(synthetic_model(torch.from_numpy(y), int(t)).numpy(), int(t), y)
+    assert np.array_equal(np.array([(a, b, int(c)) for a, b, c in o.trace]), gold[tag + "_trace"])
+    assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_bf16_model_output_promotes_like_the_reference(gold):
+    """noise_pred is bf16, latents fp32: sigma * model_output is a bf16 product (0-dim tensors do not promote)."""
+    s = UniPCMultistepScheduler(shift=3.0)
+    s.set_timesteps(4)
+    x = torch.from_numpy(gold["n4_s3_x0"].copy())
+    mo = synthetic_model(x, 999).bfloat16()
+    s._step_index = 0
+    conv = s.convert_model_output(mo, x)
+    assert conv.dtype == torch.float32
+    assert torch.equal(conv, x - (s.sigmas[0] * mo))
+    assert (s.sigmas[0] * mo).dtype == torch.bfloat16
+
+
+def test_index_for_timestep_second_match_rule():
+    s = UniPCMultistepScheduler()
+    s.set_timesteps(4)
+    s.timesteps = torch.tensor([900, 900, 500, 100])
+    assert s.index_for_timestep(900) == 1 and s.index_for_timestep(torch.tensor(500)) == 2
+    assert unipc.index_for_timestep(np.array([900, 900, 500, 100]), 900) == 1
+
+
+def test_disable_corrector_and_lower_order_final():
+    tr = unipc.step_orders(6, solver_order=3, disable_corrector=[0, 2])
+    assert [o for _, o, _ in tr] == [1, 2, 3, 3, 2, 1]
+    assert [c for _, _, c in tr] == [False, False, True, False, True, True]
+    s = UniPCMultistepScheduler(solver_order=3, disable_corrector=[0, 2])
+    s.set_timesteps(6)
+    x = torch.randn(2, 3)
+    for t in s.timesteps:
+        x = s.step(synthetic_model(x, int(t)), t, x)[0]
+    assert s.trace == tr and torch.isfinite(x).all()
+
+
+def test_get_timesteps_variants():
+    s = UniPCMultistepScheduler(shift=3.0)
+    ts, n = get_timesteps(s, num_inference_steps=10)
+    assert n == 10 and np.array_equal(ts.numpy(), unipc.make_schedule(10, 3.0)[1])
+    ts2, n2 = get_timesteps(s, num_inference_steps=10, strength=0.5)
+    assert n2 == 5 and np.array_equal(ts2.numpy(), unipc.strength_cut(ts.numpy(), 0.5))
+    s.set_timesteps(1000)
+    full = s.timesteps.clone()
+    ids = [1000, 750, 500, 250]
+    ts3, n3 = get_timesteps(s, timesteps=ids, timesteps_as_indices=True)
+    assert n3 == 4 and np.array_equal(ts3.numpy(), unipc.timesteps_as_indices(full.numpy(), ids))
+
+
+def test_expert_switch_is_integer_exact():
+    _, ts = unipc.make_schedule(50, 3.0)
+    boundary = 0.875 * 1000
+    expect = unipc.expert_and_guidance(ts, boundary, [4.0, 3.0])
+    got = [("high" if select_expert_is_high(torch.tensor(t), boundary) else "low",
+            select_guidance_scale(torch.tensor(t), boundary, [4.0, 3.0])) for t in ts]
+    assert got == expect
+    assert sum(e == "high" for e, _ in got) == int((ts >= 875).sum())
+    assert select_guidance_scale(torch.tensor(10), None, 5.0) == 5.0
