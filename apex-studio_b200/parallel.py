@@ -79,9 +79,7 @@ class ParallelContext:
         """All-gather the branch predictions inside the CFG pair; returns (cond, uncond)."""
         if self.cfg_size == 1:
             raise RuntimeError("exchange_cfg needs cfg_size == 2")
-        mine = mine.contiguous()
-        both = torch.empty((2,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        dist.all_gather_into_tensor(both, mine, group=self.cfg_group)
+        both = _all_gather_stacked(mine, 2, self.cfg_group)
         return both[0], both[1]
 
     # ------------------------------------------------------------------------------------ token shards
@@ -136,10 +134,15 @@ class ParallelContext:
         """Single all-gather over ALL ranks of equally shaped per-rank tile stacks -> [world, ...]."""
         if self.world_size == 1:
             return mine.unsqueeze(0)
-        mine = mine.contiguous()
-        out = torch.empty((self.world_size,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
-        dist.all_gather_into_tensor(out, mine, group=self.world_group)
-        return out
+        return _all_gather_stacked(mine, self.world_size, self.world_group)
+
+
+def _all_gather_stacked(mine: torch.Tensor, n: int, group) -> torch.Tensor:
+    """all_gather_into_tensor through flat 1-D views (the form every backend accepts) -> [n, *mine.shape]."""
+    flat = mine.contiguous().view(-1)
+    out = torch.empty(n * flat.numel(), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view((n,) + tuple(mine.shape))
 
 
 def plan_layout(world_size: int, use_cfg: bool) -> Tuple[int, int]:

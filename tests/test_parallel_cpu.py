@@ -1,0 +1,124 @@
+"""Multi-process host logic on CPU (gloo, world_size 2 and 4): CFG-pair exchange, Ulysses token<->head
+re-partitioning, the CFG-parallel denoise loop.  The arithmetic kernels are replaced by the oracle here
+(this file tests the HOST side of the sharding; kernels are tested in test_gpu_parity.py)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(world, fn, *args):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def _ulysses_roundtrip(rank, world, use_cfg):
+    from apex_studio_b200.parallel import ParallelContext
+
+    par = ParallelContext.create(use_cfg=use_cfg)
+    P = par.sp_size
+    heads, hd, S = 4, 8, 24
+    g = torch.Generator().manual_seed(5)
+    qkv_full = torch.randn(S, 3 * heads * hd, generator=g)       # same on every rank
+    lo, hi = par.shard_bounds(S)
+    got = par.tokens_to_heads(qkv_full[lo:hi].contiguous(), heads, hd)   # [3, S, (H/P)*hd]
+    hp = heads // P
+    for which in range(3):
+        cols = qkv_full[:, which * heads * hd:(which + 1) * heads * hd]
+        expect = cols[:, par.sp_rank * hp * hd:(par.sp_rank + 1) * hp * hd]
+        assert torch.equal(got[which], expect), (rank, which)
+    # "attention output" for my heads = q for my heads; after heads_to_tokens I must hold q of my tokens
+    back = par.heads_to_tokens(got[0].contiguous())
+    assert torch.equal(back, qkv_full[lo:hi, :heads * hd]), rank
+    full = par.gather_tokens(back)
+    assert torch.equal(full, qkv_full[:, :heads * hd])
+
+
+@pytest.mark.parametrize("world,use_cfg", [(2, False), (4, True), (4, False)])
+def test_ulysses_repartition(world, use_cfg):
+    _run(world, _ulysses_roundtrip, use_cfg)
+
+
+def _cfg_loop(rank, world):
+    """CFG-parallel moe_denoise on 2 ranks == sequential cond/uncond loop on one rank (bit for bit)."""
+    import numpy as np
+
+    import wan_dit
+    from apex_studio_b200 import denoise, ops
+    from apex_studio_b200.parallel import ParallelContext
+    from apex_studio_b200.scheduler import UniPCMultistepScheduler
+
+    ops.cfg_combine = lambda c, u, g: wan_dit.cfg_combine(c, u, g)   # oracle arithmetic on CPU
+
+    class FakeDiT:
+        def __init__(self, k):
+            self.k = k
+
+        def __call__(self, hidden_states, timestep, encoder_hidden_states, return_dict=False, parallel=None, **kw):
+            e = encoder_hidden_states.float().mean()
+            y = self.k * hidden_states.float() + 0.05 * torch.sin(hidden_states.float() * 2 + e + timestep.float().view(-1, 1, 1, 1, 1) * 1e-3)
+            return (y.to(hidden_states.dtype),)
+
+    def run(par):
+        sch = UniPCMultistepScheduler(shift=3.0)
+        sch.set_timesteps(6)
+        lat = torch.randn(1, 4, 2, 4, 4, generator=torch.Generator().manual_seed(1))
+        tr = denoise.DenoiseTrace()
+        out = denoise.moe_denoise(
+            timesteps=sch.timesteps, latents=lat, scheduler=sch, high_noise_transformer=FakeDiT(0.3),
+            low_noise_transformer=FakeDiT(0.4), boundary_timestep=875.0, guidance_scale=[4.0, 3.0],
+            transformer_kwargs=dict(encoder_hidden_states=torch.ones(1, 3, 8)),
+            unconditional_transformer_kwargs=dict(encoder_hidden_states=torch.zeros(1, 3, 8)), parallel=par, trace=tr)
+        return out, tr
+
+    par = ParallelContext.create(use_cfg=True)
+    assert (par.cfg_size, par.sp_size) == (2, 1)
+    sharded, tr_p = run(par)
+    single, tr_s = run(ParallelContext.single())
+    assert torch.equal(sharded, single)
+    assert tr_p.timesteps == tr_s.timesteps and tr_p.expert == tr_s.expert and tr_p.guidance == tr_s.guidance
+    assert tr_s.expert[0] == "high" and tr_s.expert[-1] == "low"
+    # both ranks hold identical latents without any broadcast
+    both = [torch.empty_like(sharded) for _ in range(world)]
+    dist.all_gather(both, sharded)
+    assert torch.equal(both[0], both[1])
+
+
+def test_cfg_parallel_denoise_loop():
+    _run(2, _cfg_loop)
+
+
+def test_plan_layout_and_dealing():
+    from apex_studio_b200.parallel import deal_round_robin, plan_layout
+
+    assert plan_layout(1, True) == (1, 1) and plan_layout(2, True) == (2, 1)
+    assert plan_layout(4, True) == (2, 2) and plan_layout(8, True) == (2, 4) and plan_layout(8, False) == (1, 8)
+    tiles = [deal_round_robin(28, 8, r) for r in range(8)]
+    assert sorted(sum(tiles, [])) == list(range(28)) and [len(t) for t in tiles] == [4, 4, 4, 4, 3, 3, 3, 3]
