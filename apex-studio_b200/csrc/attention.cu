@@ -15,6 +15,8 @@
 // Replaces attention_register.call(q, k, v) -- attention/functions.py:84 (`sdpa` :338-377 is the gold
 // backend) as called by transformer/wan/base/attention.py:397.
 #include "host_util.cuh"
+#include <stdlib.h>
+
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -26,7 +28,7 @@ constexpr int BKV = 128;  // keys per tile
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two [128 x 64] swizzled half tiles
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr int KV_SLOTS = 4;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 384;  // warpgroups: softmax0 | softmax1 | {TMA, MMA, 2 idle warps}
 constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -37,6 +39,54 @@ struct Params {
   float scale_log2;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Softmax of one 128-key tile for one query row (thread == row == TMEM lane).
+// VARIANT 1 (bring-up): two passes over TMEM in 32-column chunks (max, then exp), scalar fp32 math.
+// VARIANT 2 (default):  one pass -- the whole S row is loaded into registers with four back-to-back tcgen05.ld,
+//   packed fma/add (.f32x2) for the scale-and-subtract and the row sum, and POLY_PAIRS of every 16 column
+//   pairs take a Cody-Waite + cubic-polynomial exp2 on the FMA pipe instead of MUFU.EX2 (the SFU is the
+//   co-bottleneck: 128x128 exps at 16/clk/SM take as long as the two 128x128x128 MMAs of the tile).
+// ---------------------------------------------------------------------------------------------------------
+B200_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  float2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+B200_DEVICE float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  float2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// 2^x for x <= ~9 on the FMA/ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a cubic (max rel err
+// 1.0e-4, far below the bf16 rounding of P), exponent added with an integer shift-add.
+B200_DEVICE float2 exp2_poly2(float2 x) {
+  const float magic = 12582912.0f;  // 1.5 * 2^23: adding it rounds x to an integer in the low mantissa bits
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = fadd2(x, make_float2(magic, magic));
+  const float2 n = fadd2(t, make_float2(-magic, -magic));
+  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+  float2 p = ffma2(f, make_float2(0.0558263f, 0.0558263f), make_float2(0.2401537f, 0.2401537f));
+  p = ffma2(p, f, make_float2(0.6931472f, 0.6931472f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+constexpr int POLY_PAIRS = 4;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
+
+template <int VARIANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, Params p) {
@@ -85,8 +135,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Register budget per SMSP slot is 512 / 3 warps: give the two softmax warpgroups 224 registers each (a whole
+  // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 56.
+  // (setmaxnreg sits at the top of each role branch so that ptxas budgets each branch separately.)
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<80>();
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
       for (int t = 0; t < 2; ++t) {
@@ -113,6 +167,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
+    setmaxnreg_dec<80>();
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ, BKV, 0);  // B = K tile, K-major
       constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ, D, 1);    // B = V tile, MN-major
@@ -186,8 +241,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+  } else if (warp >= 10) {
+    setmaxnreg_dec<80>();  // idle warps of the third warpgroup
   } else {
     // ------------------------------------------------------------------ softmax warps
+    setmaxnreg_inc<216>();
     const int t = warp >> 2;     // query tile
     const int quad = warp & 3;   // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -200,6 +258,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int valid = p.Sk - j * BKV;  // >= 128 except possibly for the last tile
+      if constexpr (VARIANT == 2) {
+        uint32_t s[128];
+        tmem_ld_x32(s_addr + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+        tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+        tmem_ld_wait();
+        if (valid < BKV) {
+#pragma unroll
+          for (int k = 0; k < 128; ++k)
+            if (k >= valid) s[k] = 0xff800000u;  // -inf
+        }
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+              mx3 = __uint_as_float(s[3]);
+#pragma unroll
+        for (int k = 4; k < 128; k += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[k]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[k + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[k + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[k + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float m_new = fmaxf(m, mx * sl2);
+        if (j == 0) {
+          m = m_new;
+        } else if (__any_sync(0xffffffffu, (m_new - m) > RESCALE_THRESHOLD)) {
+          const float alpha = fast_exp2(m - m_new);
+          l *= alpha;
+          m = m_new;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld_x32(o_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+            tmem_st_x32(o_addr + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+        const float2 sl2_2 = make_float2(sl2, sl2);
+        const float2 negm_2 = make_float2(-m, -m);
+        float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int col = c * 32 + 2 * k;
+            const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
+            float2 e;
+            if (k < POLY_PAIRS) {
+              e = exp2_poly2(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
+            sum2 = fadd2(sum2, e);
+            pk[k] = pack_bf16x2(e.x, e.y);
+          }
+          tmem_st_x16(s_addr + c * 16, pk);
+        }
+        l += sum2.x + sum2.y;
+      } else {
       // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll 1
@@ -260,6 +382,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_x16(s_addr + c * 16, pk);
       }
       l += lsum;
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -339,14 +462,21 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_ss = o_ss;
   p.scale_log2 = scale * 1.4426950408889634f;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return B200_ERR_LAUNCH;
-    attr_done = true;
+  // B200_ATTN_VARIANT=1 selects the two-pass bring-up softmax (A/B measurements); default is variant 2.
+  static int variant = 0;
+  if (variant == 0) {
+    const char* ev = getenv("B200_ATTN_VARIANT");
+    variant = (ev && ev[0] == '1') ? 1 : 2;
+    cudaError_t e1 = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return B200_ERR_LAUNCH;
   }
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (variant == 1)
+    attn_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  else
+    attn_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -132,6 +132,40 @@ def golden_scheduler():
     print("scheduler", sorted(out)[:6], "...")
 
 
+VAE_CFG = dict(base_dim=32, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2)
+VAE_CASES = {
+    # name: (latent shape, tiling, output subsample stride)
+    "tiled": ((1, 16, 3, 36, 28), True, 3),      # tiles 32x28, 32x4, 12x28, 12x4 (stride 24) -> blends + crops
+    "untiled": ((1, 16, 4, 20, 16), False, 2),   # one tile, 13 output frames
+}
+
+
+def golden_vae():
+    """Reference AutoencoderKLWan (streaming, feat_cache) on a reduced-width decoder (base_dim 32) with the
+    production tiling parameters (256/192 px).  Outputs are stored spatially subsampled to keep fixtures small."""
+    import wan_vae
+
+    v = bootstrap.ref("src.vae.wan.model")
+    w = wan_vae.make_weights(base_dim=VAE_CFG["base_dim"], seed=7)
+    out = {}
+    for name, (shape, tiling, sub) in VAE_CASES.items():
+        lat = torch.randn(shape, generator=torch.Generator().manual_seed(11))
+        out[name + "_latents"] = f32(lat)
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            vae = v.AutoencoderKLWan(**VAE_CFG, temperal_downsample=[False, True, True]).eval()
+            vae.load_state_dict(w, strict=False)
+            vae = vae.to(dt)
+            with torch.no_grad():
+                z = vae.denormalize_latents(lat).to(dt)     # base_engine.py:2040-2048
+                if tiling:
+                    vae.enable_tiling()
+                y = vae.decode(z, return_dict=False)[0]
+            out[f"{name}_out_{tag}"] = f32(y[..., ::sub, ::sub])
+            out[f"{name}_shape"] = np.array(y.shape)
+    np.savez_compressed(os.path.join(GOLDEN, "wan_vae.npz"), **out)
+    print("vae", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae"]
