@@ -1,0 +1,370 @@
+// b200_conv3d_cl: causal 3-D convolution on channels-last activations as an implicit GEMM on tcgen05.
+//
+//   y[t, h, w, :] = bias + sum_{kt,kh,kw} W[kt,kh,kw] . x[t + kt - (KT-1), h + kh - KH/2, w + kw - KW/2, :]
+//
+// (zero outside the volume: KT-1 zero frames on the LEFT of time only -- WanCausalConv3d, vae/wan/model.py:136-185 --
+// and symmetric zero padding in H/W.)  One kernel covers the 3x3x3 convs of the residual blocks, conv_in/conv_out, the
+// (3,1,1) time_conv of upsample3d and the per-frame 3x3 Conv2d of WanResample.
+//
+// GEMM view: M = output pixels (tiles of 128 = BH rows x BW columns of ONE frame), N = C_out, K = taps x C_in.
+// The A operand of tap (kt,kh,kw) is a shifted [BH x BW x BK] window of x, fetched by ONE 4-D TMA box whose
+// out-of-bounds elements (halo, causal left pad) are zero-filled by the TMA unit -- no im2col buffer, no padded copy.
+// The B operand is the [BN x BK] slice of the tap's weight matrix (host layout [tap][C_out][C_in]).
+// Warp roles / pipeline are those of linear.cu: warp 0 TMA, warp 1 MMA (fp32 accumulators in TMEM, two buffers),
+// warps 2-5 epilogue (bias, optional residual add, bf16 channels-last store, or planar store for conv_out, or the
+// 2x temporal interleave of upsample3d, vae/wan/model.py:332-334).
+#include "host_util.cuh"
+#include "sm100_ptx.cuh"
+
+namespace b200 {
+namespace conv {
+
+constexpr int BM = 128;
+constexpr int BN_MAX = 256;
+constexpr int NUM_THREADS = 192;
+
+template <int BK>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN_MAX * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BK == 64) ? 4 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t SBO = 8 * BK * 2;          // bytes between 8-row groups (dense rows of BK bf16)
+  static constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
+};
+
+struct Params {
+  int T, H, W, Cin, Cout;     // output volume == input volume (stride 1)
+  int KT, KH, KW;
+  int BW, BH, BN;             // pixel tile = BH x BW (BH*BW == 128), N tile
+  int tiles_w, tiles_h, tiles_n;
+  const __nv_bfloat16* bias;      // [Cout] or null
+  const __nv_bfloat16* residual;  // channels-last [T,H,W,Cout] or null
+  void* out;
+  int out_mode;               // 0: channels-last bf16 [T',H,W,Csplit]; 1: planar bf16 [Cvalid,T,H,W]
+  int out_t_mul, out_t_off;   // destination frame = t * out_t_mul + out_t_off + (n / Csplit)
+  int Csplit;                 // channels per destination frame (== Cout unless temporal interleave)
+  int Cvalid;                 // number of real output channels (planar mode; <= Cout)
+};
+
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((Cfg<BK>::SBO >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= Cfg<BK>::LAYOUT << 61;
+  return d;
+}
+
+B200_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int BK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, Params p) {
+  using C = Cfg<BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* acc_full = bars + 2 * C::STAGES;
+  uint64_t* acc_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int taps = p.KT * p.KH * p.KW;
+  const int kchunks = p.Cin / BK;
+  const int tiles_per_frame = p.tiles_h * p.tiles_w;
+  const int total_tiles = p.T * tiles_per_frame * p.tiles_n;
+  const uint32_t stage_tx = static_cast<uint32_t>((BM * BK + p.BN * BK) * 2);
+
+  // tile -> (n tile, frame, pixel-tile origin); n fastest so that neighbouring CTAs share the activation window
+  auto decode = [&](int tile, int& tn, int& t, int& h0, int& w0) {
+    tn = tile % p.tiles_n;
+    int m = tile / p.tiles_n;
+    t = m / tiles_per_frame;
+    int r = m - t * tiles_per_frame;
+    h0 = (r / p.tiles_w) * p.BH;
+    w0 = (r % p.tiles_w) * p.BW;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tn, t, h0, w0;
+        decode(tile, tn, t, h0, w0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kt = tap / (p.KH * p.KW);
+          const int kh = (tap / p.KW) % p.KH;
+          const int kw = tap % p.KW;
+          const int ti = t + kt - (p.KT - 1);
+          const int hi = h0 + kh - p.KH / 2;
+          const int wi = w0 + kw - p.KW / 2;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE_BYTES;
+            uint8_t* sb = sa + C::A_BYTES;
+            mbar_arrive_expect_tx(&full[stage], stage_tx);
+            tma_load_4d(sa, &tmX, &full[stage], kc * BK, wi, hi, ti);
+            tma_load_2d(sb, &tmW, &full[stage], kc * BK, tap * p.Cout + tn * p.BN);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16_f32(BM, p.BN, 0);
+      const int k_iters = taps * kchunks;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN_MAX;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss(d_tmem, make_desc<BK>(a_addr + k * 32), make_desc<BK>(b_addr + k * 32), idesc,
+                    (ki | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int64_t frame_px = static_cast<int64_t>(p.H) * p.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int tn, t, h0, w0;
+      decode(tile, tn, t, h0, w0);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const int r = quad * 32 + lane;
+      const int h = h0 + r / p.BW;
+      const int w = w0 + r % p.BW;
+      const bool ok = (h < p.H) && (w < p.W);
+      const int64_t pix = static_cast<int64_t>(h) * p.W + w;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN_MAX;
+      const int n_base = tn * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t rr[16];
+        tmem_ld_x16(t_addr + c0, rr);
+        tmem_ld_wait();
+        const int n0 = n_base + c0;  // first output channel of this 16-wide chunk
+        if (n0 >= p.Cout) break;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+        if (p.bias != nullptr) {
+          const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 b = __ldg(bp + q);
+            v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
+            v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
+            v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
+            v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
+          }
+        }
+        if (!ok) continue;
+        if (p.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (static_cast<int64_t>(t) * frame_px + pix) * p.Cout + n0);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 b = rp[q];
+            v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
+            v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
+            v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
+            v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
+          }
+        }
+        if (p.out_mode == 0) {
+          const int g = n0 / p.Csplit;
+          const int cdst = n0 - g * p.Csplit;
+          const int64_t tf = static_cast<int64_t>(t) * p.out_t_mul + p.out_t_off + g;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (tf * frame_px + pix) * p.Csplit + cdst;
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]);  o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]);  o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]);  o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          reinterpret_cast<uint4*>(op)[0] = o0;
+          reinterpret_cast<uint4*>(op)[1] = o1;
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < p.Cvalid)
+              op[(static_cast<int64_t>(n0 + j) * p.T + t) * frame_px + pix] = __float2bfloat16(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline int make_tmap_bf16_sw(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_elems, const uint32_t* box, bool sw64) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return B200_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200_ERR_ALIGN;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_elems[i] * 2;
+      if (gstr[i - 1] % 16 != 0) return B200_ERR_ALIGN;
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[apex_b200] cuTensorMapEncodeTiled (conv) failed: %d\n", (int)r);
+    return B200_ERR_TMAP;
+  }
+  return B200_OK;
+}
+
+template <int BK>
+int launch(const void* x, const void* wt, Params& p, cudaStream_t st) {
+  using C = Cfg<BK>;
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T};
+    uint64_t str[4] = {1, (uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    int rc = make_tmap_bf16_sw(&tmX, x, 4, dims, str, box, BK == 32);
+    if (rc) return rc;
+  }
+  {
+    const int taps = p.KT * p.KH * p.KW;
+    uint64_t dims[2] = {(uint64_t)p.Cin, (uint64_t)taps * p.Cout};
+    uint64_t str[2] = {1, (uint64_t)p.Cin};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)p.BN};
+    int rc = make_tmap_bf16_sw(&tmW, wt, 2, dims, str, box, BK == 32);
+    if (rc) return rc;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(conv3d_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_LAUNCH;
+    attr_done = true;
+  }
+  const int total = p.T * p.tiles_h * p.tiles_w * p.tiles_n;
+  const int grid = total < num_sms() ? total : num_sms();
+  conv3d_kernel<BK><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmX, tmW, p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // namespace conv
+}  // namespace b200
+
+extern "C" int b200_conv3d_cl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T,
+                              int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul,
+                              int out_t_off, int c_split, int c_valid, void* stream) {
+  using namespace b200;
+  using namespace b200::conv;
+  if (!x || !w || !out) return B200_ERR_ARG;
+  if (T <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return B200_ERR_SHAPE;
+  if (KT < 1 || KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1)) return B200_ERR_SHAPE;
+  if ((Cin % 32) || (Cout % 16)) return B200_ERR_SHAPE;
+  if (out_mode != 0 && out_mode != 1) return B200_ERR_ARG;
+  if (c_split <= 0 || (Cout % c_split) || (c_split % 16)) return B200_ERR_SHAPE;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return B200_ERR_ALIGN;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || c_split != Cout)) return B200_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(out) & 15) return B200_ERR_ALIGN;
+  Params p;
+  p.T = T; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.KT = KT; p.KH = KH; p.KW = KW;
+  int bw = 1;
+  while (bw * 2 <= W && bw * 2 <= BM) bw *= 2;
+  p.BW = bw;
+  p.BH = BM / bw;
+  // N tile: the largest divisor of Cout that is a multiple of 16, at most 256 and inside one interleave group
+  int bn = 0;
+  for (int cand = 256; cand >= 16; cand -= 16)
+    if (Cout % cand == 0 && c_split % cand == 0) { bn = cand; break; }
+  if (bn == 0) return B200_ERR_SHAPE;
+  p.BN = bn;
+  p.tiles_w = (W + p.BW - 1) / p.BW;
+  p.tiles_h = (H + p.BH - 1) / p.BH;
+  p.tiles_n = Cout / bn;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = out;
+  p.out_mode = out_mode;
+  p.out_t_mul = out_t_mul; p.out_t_off = out_t_off;
+  p.Csplit = c_split; p.Cvalid = c_valid;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (Cin % 64 == 0) return launch<64>(x, w, p, st);
+  return launch<32>(x, w, p, st);
+}

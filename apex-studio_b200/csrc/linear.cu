@@ -35,6 +35,7 @@ struct Params {
   void* C;
   int64_t ldc;
   int epi;
+  int bias_row;
   int tiles_m, tiles_n;
 };
 
@@ -175,7 +176,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const bool full_chunk = (col0 + 32 <= p.N);
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && p.bias_row) {
+          const float br = row_ok ? __bfloat162float(p.bias[row]) : 0.f;  // per-ROW bias (transposed projections)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += br;
+        } else if (p.bias != nullptr) {
           if (full_chunk) {
             const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
@@ -286,6 +291,8 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   using namespace b200;
   using namespace b200::linear;
   if (!A || !W || !C) return B200_ERR_ARG;
+  const int bias_row = (epilogue & B200_EPI_ROW_BIAS) ? 1 : 0;
+  epilogue &= ~B200_EPI_ROW_BIAS;
   if (epilogue < 0 || epilogue > 3) return B200_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return B200_ERR_SHAPE;
   if ((K % 8) || (lda % 8) || (ldw % 8)) return B200_ERR_ALIGN;
@@ -316,6 +323,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.C = C;
   p.ldc = ldc;
   p.epi = epilogue;
+  p.bias_row = bias_row;
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + BN - 1) / BN;
   const int total = p.tiles_m * p.tiles_n;

@@ -86,10 +86,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: 
 # linear with fused epilogue
 # ---------------------------------------------------------------------------------------------------
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS,
-           out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+           row_bias: bool = False) -> torch.Tensor:
     """out = epilogue(x @ weight^T + bias).  x [..., K] (last dim contiguous), weight [N, K].
 
     EPI_GATE_RES: ``out`` is the residual stream, updated in place: out += gate * (x @ W^T + bias).
+    ``row_bias``: bias has one entry per ROW of x (transposed projections) instead of per output column.
     """
     _require_cuda_bf16("x", x)
     _require_cuda_bf16("weight", weight)
@@ -124,7 +126,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
             raise ValueError(f"gate must be a contiguous [{N}] vector")
     lib = _lib.load()
     rc = lib.b200_linear(x2.data_ptr(), weight.data_ptr(), _ptr(bias), o2.data_ptr(), _ptr(gate), M, N, K,
-                         x2.stride(0), weight.stride(0), o2.stride(0), epilogue, _stream())
+                         x2.stride(0), weight.stride(0), o2.stride(0), epilogue | (16 if row_bias else 0), _stream())
     _lib.check(rc, "b200_linear")
     _count()
     return out

@@ -1,0 +1,366 @@
+"""Wan 3-D causal VAE -- decode path on the B200 kernels.
+
+Host-side mirror of the decode half of the reference's ``AutoencoderKLWan`` (apps/api/src/vae/wan/model.py:1083;
+``decode`` :1378, ``_decode`` :1333-1375, ``tiled_decode`` :1516-1623, ``denormalize_latents`` :1649-1659) for the
+non-residual decoder the Wan 2.1 / 2.2-A14B pipelines use (``WanDecoder3d`` :881-1021): same state-dict keys, the
+``decode(z, return_dict=False)[0]`` / ``denormalize_latents`` / ``enable_tiling`` / ``.dtype`` / ``.config`` surface
+``BaseEngine.vae_decode`` (engine/base_engine.py:2030-2059) relies on, so it can be registered as
+``VAE_REGISTRY["wan_b200"]``.
+
+Design (DESIGN.md section "VAE"):
+* activations are channels-last bf16 ``[T, H, W, C]`` so that every causal conv is an implicit GEMM whose A operand
+  is a TMA box with hardware zero fill for the spatial halo and the causal left pad (csrc/conv.cu);
+* the reference's frame-by-frame ``feat_cache`` streaming equals one causal convolution over the whole time axis
+  (proved against the reference in tests/test_oracle_vae.py), so a tile is decoded for ALL frames at once:
+  ~60 launches per tile instead of ~35 convs x 21 frames;
+* the 32x32-latent / stride-24 tiling, the in-place blend order and the crop are reproduced exactly (tiles see zero
+  padding at their borders in the reference, so decoding untiled would NOT give the same pixels);
+* tiles are independent until the blend: with N GPUs they are dealt round-robin and reassembled by ONE all-gather.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib, ops
+from ..parallel import ParallelContext, deal_round_robin
+
+
+@dataclass
+class WanVAEConfig:
+    """Constructor arguments of the reference class that matter for decode (vae/wan/model.py:1100-1160)."""
+    base_dim: int = 96
+    decoder_base_dim: Optional[int] = None
+    z_dim: int = 16
+    dim_mult: Sequence[int] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    temperal_downsample: Sequence[bool] = (False, True, True)
+    latents_mean: Sequence[float] = (-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134,
+                                     -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921)
+    latents_std: Sequence[float] = (2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743, 3.2687, 2.1526,
+                                    2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.916)
+    is_residual: bool = False
+    out_channels: int = 3
+    patch_size: Optional[int] = None
+    scale_factor_temporal: int = 4
+    scale_factor_spatial: int = 8
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI
+# ---------------------------------------------------------------------------------------------------------
+def conv3d_cl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], taps: Tuple[int, int, int], cout: int, *,
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, planar_channels: int = 0,
+              interleave: bool = False) -> torch.Tensor:
+    """x [T,H,W,Cin] channels-last bf16, w [taps*cout, Cin] tap-major.  Returns [T,H,W,cout] (or, with
+    ``interleave``, writes frames 1.. of ``out`` [1+2T,H,W,cout/2]; or planar [planar_channels,T,H,W])."""
+    T, H, W, cin = x.shape
+    kt, kh, kw = taps
+    if not x.is_contiguous():
+        raise ValueError("conv3d_cl needs a contiguous channels-last input")
+    if planar_channels:
+        if out is None:
+            out = torch.empty(planar_channels, T, H, W, dtype=torch.bfloat16, device=x.device)
+        mode, tmul, toff, csplit, cvalid = 1, 1, 0, cout, planar_channels
+    elif interleave:
+        if out is None:
+            raise ValueError("interleave writes into an existing [1+2T,H,W,C/2] buffer")
+        mode, tmul, toff, csplit, cvalid = 0, 2, 1, cout // 2, cout
+    else:
+        if out is None:
+            out = torch.empty(T, H, W, cout, dtype=torch.bfloat16, device=x.device)
+        mode, tmul, toff, csplit, cvalid = 0, 1, 0, cout, cout
+    lib = _lib.load()
+    rc = lib.b200_conv3d_cl(x.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(),
+                            None if residual is None else residual.data_ptr(), out.data_ptr(), T, H, W, cin, cout, kt, kh,
+                            kw, mode, tmul, toff, csplit, cvalid, _stream())
+    _lib.check(rc, "b200_conv3d_cl")
+    ops._count()
+    return out
+
+
+def rmsnorm_silu_cl(x: torch.Tensor, gamma: torch.Tensor, silu: bool = True, out: Optional[torch.Tensor] = None):
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    lib = _lib.load()
+    rc = lib.b200_rmsnorm_silu_cl(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), x.numel() // C, C, int(silu), _stream())
+    _lib.check(rc, "b200_rmsnorm_silu_cl")
+    ops._count()
+    return out
+
+
+def upsample2x_cl(x: torch.Tensor) -> torch.Tensor:
+    T, H, W, C = x.shape
+    out = torch.empty(T, 2 * H, 2 * W, C, dtype=x.dtype, device=x.device)
+    lib = _lib.load()
+    rc = lib.b200_upsample2x_cl(x.data_ptr(), out.data_ptr(), T, H, W, C, _stream())
+    _lib.check(rc, "b200_upsample2x_cl")
+    ops._count()
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float) -> torch.Tensor:
+    rows, cols = s.shape
+    p = torch.empty(rows, cols, dtype=torch.bfloat16, device=s.device)
+    lib = _lib.load()
+    rc = lib.b200_softmax_rows(s.data_ptr(), p.data_ptr(), rows, cols, s.stride(0), p.stride(0), float(scale), _stream())
+    _lib.check(rc, "b200_softmax_rows")
+    ops._count()
+    return p
+
+
+def blend_tile(tile: torch.Tensor, up: Optional[torch.Tensor], left: Optional[torch.Tensor], frame: torch.Tensor,
+               blend: int, crop: int, y0: int, x0: int) -> None:
+    """tile/up/left: planar [3, T, th, tw] bf16 (contiguous); frame: [3, T, OH, OW]."""
+    planes = tile.shape[0] * tile.shape[1]
+    th, tw = tile.shape[-2:]
+    uh, uw = (up.shape[-2], up.shape[-1]) if up is not None else (0, 0)
+    lh, lw = (left.shape[-2], left.shape[-1]) if left is not None else (0, 0)
+    lib = _lib.load()
+    rc = lib.b200_blend_tile(tile.data_ptr(), None if up is None else up.data_ptr(),
+                             None if left is None else left.data_ptr(), frame.data_ptr(), planes, th, tw, uh, uw, lh, lw,
+                             blend, min(crop, th), min(crop, tw), y0, x0, frame.shape[-2], frame.shape[-1], _stream())
+    _lib.check(rc, "b200_blend_tile")
+    ops._count()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the decoder
+# ---------------------------------------------------------------------------------------------------------
+class AutoencoderKLWan:
+    """Decode-only B200 implementation (see module docstring)."""
+
+    def __init__(self, config: Optional[WanVAEConfig] = None, **kwargs):
+        self.config = config or WanVAEConfig(**kwargs)
+        if self.config.is_residual or self.config.patch_size is not None:
+            raise ValueError("only the non-residual Wan 2.1 / 2.2-A14B VAE decoder is implemented (is_residual=False)")
+        self.dtype = torch.bfloat16
+        self.device = None
+        self.w: Dict[str, torch.Tensor] = {}
+        self.use_tiling = False
+        self.tile_sample_min_height = self.tile_sample_min_width = 256
+        self.tile_sample_stride_height = self.tile_sample_stride_width = 192
+        self.spatial_compression_ratio = self.config.scale_factor_spatial
+        c = self.config
+        d = c.decoder_base_dim or c.base_dim
+        self.dims = [d * u for u in [c.dim_mult[-1]] + list(c.dim_mult[::-1])]
+        self.temporal_upsample = list(c.temperal_downsample[::-1])
+
+    # -------------------------------------------------------------------------------- weights
+    @staticmethod
+    def _tap_major(w: torch.Tensor, cin_pad: int = 0, cout_pad: int = 0) -> torch.Tensor:
+        """[Cout,Cin,kt,kh,kw] or [Cout,Cin,kh,kw] -> [taps*Cout', Cin'] (tap-major, zero padded channels)."""
+        if w.dim() == 4:
+            w = w.unsqueeze(2)
+        cout, cin = w.shape[:2]
+        if cin_pad > cin:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, cin_pad - cin))
+        if cout_pad > cout:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, 0, 0, cout_pad - cout))
+        taps = w.shape[2] * w.shape[3] * w.shape[4]
+        return w.permute(2, 3, 4, 0, 1).reshape(taps * w.shape[0], w.shape[1]).contiguous()
+
+    def load_state_dict(self, state: Dict[str, torch.Tensor], device="cuda", strict: bool = False):
+        """Reference state dict (decoder.* and post_quant_conv.*; encoder keys are ignored) -> bf16 device tensors in
+        the kernels' layouts.  Channel padding: conv_in consumes 32 channels (z_dim 16 + 16 zero channels produced
+        by a zero-padded post_quant_conv), conv_out produces 16 (3 real)."""
+        dev = torch.device(device)
+        self.device = dev
+        bf = torch.bfloat16
+        w: Dict[str, torch.Tensor] = {}
+        z = self.config.z_dim
+        zp = max(32, (z + 31) // 32 * 32)
+        self.z_pad = zp
+        for k, v in state.items():
+            if not (k.startswith("decoder.") or k.startswith("post_quant_conv.")):
+                continue
+            v = v.detach().to(dev, torch.float32)
+            if k == "post_quant_conv.weight":
+                w[k] = torch.nn.functional.pad(v.reshape(z, z), (0, 0, 0, zp - z)).to(bf).contiguous()   # [zp, z]
+            elif k == "post_quant_conv.bias":
+                w[k] = torch.nn.functional.pad(v, (0, zp - z)).to(bf).contiguous()
+            elif k == "decoder.conv_in.weight":
+                w[k] = self._tap_major(v, cin_pad=zp).to(bf)
+            elif k == "decoder.conv_out.weight":
+                w[k] = self._tap_major(v, cout_pad=16).to(bf)
+            elif k == "decoder.conv_out.bias":
+                w[k] = torch.nn.functional.pad(v, (0, 16 - v.numel())).to(bf).contiguous()
+            elif k.endswith("conv_shortcut.weight") or k.endswith("to_qkv.weight") or k.endswith("proj.weight"):
+                w[k] = v.reshape(v.shape[0], v.shape[1]).to(bf).contiguous()                              # 1x1 -> linear
+            elif k.endswith(".weight") and v.dim() >= 4:
+                w[k] = self._tap_major(v).to(bf)
+            elif k.endswith("gamma"):
+                w[k] = v.reshape(-1).to(bf).contiguous()
+            else:
+                w[k] = v.to(bf).contiguous()
+        self.w = w
+        return [], []
+
+    # -------------------------------------------------------------------------------- reference API surface
+    def enable_tiling(self, tile_sample_min_height=None, tile_sample_min_width=None, tile_sample_stride_height=None,
+                      tile_sample_stride_width=None) -> None:
+        self.use_tiling = True
+        self.tile_sample_min_height = tile_sample_min_height or self.tile_sample_min_height
+        self.tile_sample_min_width = tile_sample_min_width or self.tile_sample_min_width
+        self.tile_sample_stride_height = tile_sample_stride_height or self.tile_sample_stride_height
+        self.tile_sample_stride_width = tile_sample_stride_width or self.tile_sample_stride_width
+
+    def disable_tiling(self) -> None:
+        self.use_tiling = False
+
+    def denormalize_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """vae/wan/model.py:1649-1659 (in the latents' own dtype, fp32 in the pipeline)."""
+        c = self.config
+        mean = torch.tensor(c.latents_mean).view(1, c.z_dim, 1, 1, 1).to(latents.device, latents.dtype)
+        std = 1.0 / torch.tensor(c.latents_std).view(1, c.z_dim, 1, 1, 1).to(latents.device, latents.dtype)
+        return latents / std + mean
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    # -------------------------------------------------------------------------------- blocks
+    def _res_block(self, x: torch.Tensor, p: str) -> torch.Tensor:
+        w = self.w
+        cout = w[p + ".conv1.bias"].numel()
+        if (p + ".conv_shortcut.weight") in w:
+            h = ops.linear(x, w[p + ".conv_shortcut.weight"], w[p + ".conv_shortcut.bias"])
+        else:
+            h = x
+        n = rmsnorm_silu_cl(x, w[p + ".norm1.gamma"])
+        y = conv3d_cl(n, w[p + ".conv1.weight"], w[p + ".conv1.bias"], (3, 3, 3), cout)
+        del n
+        n = rmsnorm_silu_cl(y, w[p + ".norm2.gamma"], out=y)
+        return conv3d_cl(n, w[p + ".conv2.weight"], w[p + ".conv2.bias"], (3, 3, 3), cout, residual=h)
+
+    def _attn_block(self, x: torch.Tensor, p: str) -> torch.Tensor:
+        """Single-head attention over the H*W positions of each frame (head dim = C), x += proj(attn)."""
+        w = self.w
+        T, H, W, C = x.shape
+        N = H * W
+        xn = rmsnorm_silu_cl(x, w[p + ".norm.gamma"], silu=False)
+        wq, bq = w[p + ".to_qkv.weight"], w[p + ".to_qkv.bias"]
+        scale = C ** -0.5
+        for t in range(T):
+            xt = xn[t].view(N, C)
+            qk = ops.linear(xt, wq[:2 * C], bq[:2 * C])                                   # [N, 2C]
+            vT = ops.linear(wq[2 * C:], xt, bq[2 * C:], row_bias=True)                     # [C, N] = V^T
+            s = ops.linear(qk[:, :C], qk[:, C:], None, epilogue=ops.EPI_BIAS_F32)           # [N, N] fp32 scores
+            pm = softmax_rows(s, scale)
+            o = ops.linear(pm, vT)                                                         # [N, C]
+            ops.linear(o, w[p + ".proj.weight"], w[p + ".proj.bias"], epilogue=ops.EPI_GATE_RES, out=x[t].view(N, C),
+                       gate=None)
+        return x
+
+    def _upsample(self, x: torch.Tensor, p: str, temporal: bool) -> torch.Tensor:
+        w = self.w
+        T, H, W, C = x.shape
+        if temporal and T > 1:
+            y = torch.empty(1 + 2 * (T - 1), H, W, C, dtype=x.dtype, device=x.device)
+            y[0].copy_(x[0])
+            conv3d_cl(x[1:], w[p + ".time_conv.weight"], w[p + ".time_conv.bias"], (3, 1, 1), 2 * C, out=y, interleave=True)
+            x = y
+        u = upsample2x_cl(x)
+        return conv3d_cl(u, w[p + ".resample.1.weight"], w[p + ".resample.1.bias"], (1, 3, 3), C // 2)
+
+    def decode_tile(self, z: torch.Tensor) -> torch.Tensor:
+        """z [zc, T, h, w] (one latent tile, all frames) -> planar bf16 [3, 1+4(T-1), 8h, 8w] (pre-clamp)."""
+        w = self.w
+        zc, T, h, wd = z.shape
+        x = z.permute(1, 2, 3, 0).to(torch.bfloat16).contiguous()                          # [T,h,w,zc]
+        x = ops.linear(x.view(-1, zc), w["post_quant_conv.weight"], w["post_quant_conv.bias"]).view(T, h, wd, self.z_pad)
+        x = conv3d_cl(x, w["decoder.conv_in.weight"], w["decoder.conv_in.bias"], (3, 3, 3), self.dims[0])
+        x = self._res_block(x, "decoder.mid_block.resnets.0")
+        x = self._attn_block(x, "decoder.mid_block.attentions.0")
+        x = self._res_block(x, "decoder.mid_block.resnets.1")
+        n_up = len(self.config.dim_mult)
+        for i in range(n_up):
+            for j in range(self.config.num_res_blocks + 1):
+                x = self._res_block(x, f"decoder.up_blocks.{i}.resnets.{j}")
+            if i != n_up - 1:
+                x = self._upsample(x, f"decoder.up_blocks.{i}.upsamplers.0", self.temporal_upsample[i])
+        x = rmsnorm_silu_cl(x, w["decoder.norm_out.gamma"], out=x)
+        return conv3d_cl(x, w["decoder.conv_out.weight"], w["decoder.conv_out.bias"], (3, 3, 3), 16,
+                         planar_channels=self.config.out_channels)
+
+    # -------------------------------------------------------------------------------- decode
+    @torch.inference_mode()
+    def decode(self, z: torch.Tensor, return_dict: bool = False, parallel: Optional[ParallelContext] = None):
+        """z [B, zc, T, H, W] -> [B, 3, 1+4(T-1), 8H, 8W] bf16 in [-1, 1]."""
+        if not self.w:
+            raise RuntimeError("weights not loaded: call load_state_dict()")
+        outs = [self._decode_one(z[b].to(self.device), parallel) for b in range(z.shape[0])]
+        out = torch.stack(outs, dim=0)
+        if return_dict:
+            return {"sample": out}
+        return (out,)
+
+    def _decode_one(self, z: torch.Tensor, par: Optional[ParallelContext]) -> torch.Tensor:
+        zc, T, H, W = z.shape
+        r = self.spatial_compression_ratio
+        tmin_h, tmin_w = self.tile_sample_min_height // r, self.tile_sample_min_width // r
+        if not (self.use_tiling and (W > tmin_w or H > tmin_h)):
+            return torch.clamp(self.decode_tile(z), min=-1.0, max=1.0)
+        return self.tiled_decode(z, par)
+
+    def tile_grid(self, H: int, W: int) -> List[Tuple[int, int]]:
+        r = self.spatial_compression_ratio
+        sh, sw = self.tile_sample_stride_height // r, self.tile_sample_stride_width // r
+        return [(i, j) for i in range(0, H, sh) for j in range(0, W, sw)]
+
+    def tiled_decode(self, z: torch.Tensor, par: Optional[ParallelContext] = None) -> torch.Tensor:
+        """vae/wan/model.py:1516-1623: 32x32-latent tiles at stride 24, in-place blends in row-major tile order,
+        crop to the stride, clamp.  Tiles are dealt round-robin over the ranks of ``par`` and all-gathered once."""
+        zc, T, H, W = z.shape
+        r = self.spatial_compression_ratio
+        tmin_h, tmin_w = self.tile_sample_min_height // r, self.tile_sample_min_width // r
+        sh, sw = self.tile_sample_stride_height, self.tile_sample_stride_width
+        blend_h, blend_w = self.tile_sample_min_height - sh, self.tile_sample_min_width - sw
+        if blend_h != blend_w or sh != sw:
+            raise ValueError("non-square tiling parameters are not implemented")
+        grid = self.tile_grid(H, W)
+        ncols = len(range(0, W, sw // r))
+        world = par.world_size if par is not None else 1
+        rank = par.rank if par is not None else 0
+        mine = deal_round_robin(len(grid), world, rank)
+        T_out = 1 + self.config.scale_factor_temporal * (T - 1)
+        tiles: Dict[int, torch.Tensor] = {}
+        for idx in mine:
+            i, j = grid[idx]
+            tiles[idx] = self.decode_tile(z[:, :, i:i + tmin_h, j:j + tmin_w].contiguous())
+        if world > 1:
+            tiles = self._allgather_tiles(tiles, grid, H, W, T_out, par)
+        frame = torch.empty(self.config.out_channels, T_out, H * r, W * r, dtype=torch.bfloat16, device=z.device)
+        for idx, (i, j) in enumerate(grid):
+            ri, cj = idx // ncols, idx % ncols
+            up = tiles[idx - ncols] if ri > 0 else None
+            left = tiles[idx - 1] if cj > 0 else None
+            blend_tile(tiles[idx], up, left, frame, blend_h, sh, ri * sh, cj * sw)
+        return frame
+
+    def _allgather_tiles(self, tiles, grid, H, W, T_out, par: ParallelContext):
+        """Pad every rank's tiles to the full tile size, ONE all-gather, slice back to the true tile shapes."""
+        r = self.spatial_compression_ratio
+        th, tw = self.tile_sample_min_height, self.tile_sample_min_width
+        per_rank = (len(grid) + par.world_size - 1) // par.world_size
+        buf = torch.zeros(per_rank, self.config.out_channels, T_out, th, tw, dtype=torch.bfloat16, device=self.device)
+        for slot, idx in enumerate(sorted(tiles)):
+            t = tiles[idx]
+            buf[slot, :, :, :t.shape[-2], :t.shape[-1]] = t
+        allbuf = par.allgather_frames(buf)                                   # [world, per_rank, 3, T, th, tw]
+        out = {}
+        for idx, (i, j) in enumerate(grid):
+            src, slot = idx % par.world_size, idx // par.world_size
+            hh = min(th, (H - i) * r)
+            ww = min(tw, (W - j) * r)
+            out[idx] = allbuf[src, slot, :, :, :hh, :ww].contiguous()
+        return out

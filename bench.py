@@ -270,12 +270,14 @@ def run_b200_arm(args):
         sampler.start()
     launches0 = ops.launch_count
     timed_attention.on = True
+    torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         one_step(False)
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     timed_attention.on = False
     launches = ops.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None

@@ -65,6 +65,9 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, i
 #define B200_EPI_GELU_TANH 1
 #define B200_EPI_GATE_RES 2
 #define B200_EPI_BIAS_F32 3
+/* OR-ed into `epilogue`: bias is indexed by ROW ([M]) instead of by column -- used for transposed projections
+ * (V^T = W_v x^T + b_v of the VAE mid-block attention, vae/wan/model.py:470-478). */
+#define B200_EPI_ROW_BIAS 16
 int b200_linear(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N, int K,
                 int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream);
 
@@ -107,6 +110,45 @@ int b200_gate_residual(void* h, const void* y, const void* gate, int rows, int d
  * which the scheduler then consumes (scheduler/unipc.py:317).
  */
 int b200_cfg_combine(const void* cond, const void* uncond, void* out, float guidance, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Wan 3D-VAE decode (AutoencoderKLWan.decode, vae/wan/model.py:1378; BaseEngine.vae_decode, engine/base_engine.py:2030).
+ * Activations are channels-last bf16 [T, H, W, C] (one spatial tile of one video at a time).
+ * --------------------------------------------------------------------------------------------------------- */
+
+/*
+ * Causal 3-D convolution (WanCausalConv3d, vae/wan/model.py:136-185; also the per-frame Conv2d of WanResample
+ * :291-353 with KT = 1) as an implicit GEMM on the tensor cores:
+ *   y[t,h,w,:] = bias + sum_{kt,kh,kw} W[kt,kh,kw] x[t+kt-(KT-1), h+kh-KH/2, w+kw-KW/2, :]   (zero outside the volume)
+ * x: [T,H,W,Cin]; w: [KT*KH*KW, Cout, Cin] (tap-major, host re-layout of the reference's [Cout,Cin,KT,KH,KW]);
+ * bias: [Cout] or NULL; residual: [T,H,W,Cout] added to the result or NULL (WanResidualBlock `x + h`, :441).
+ * out_mode 0: channels-last bf16; output channel n goes to frame t*out_t_mul + out_t_off + n / c_split, channel
+ *             n % c_split (c_split = Cout, mul = 1, off = 0 for a plain conv; c_split = Cout/2, mul = 2, off = 1 for
+ *             the 2x temporal interleave of upsample3d's time_conv, :332-334).
+ * out_mode 1: planar bf16 [c_valid, T, H, W] (conv_out; channels >= c_valid are padding).
+ * Cin % 32 == 0, Cout % 16 == 0, KH and KW odd.
+ */
+int b200_conv3d_cl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T, int H, int W,
+                   int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul, int out_t_off, int c_split,
+                   int c_valid, void* stream);
+
+/* y = x / max(||x||_2 over channels, 1e-12) * sqrt(C) * gamma, then SiLU if `silu` (WanRMS_norm :216-222 + the
+ * nonlinearity at :404-405, :1005-1006); x, y: [pixels, C]; gamma: [C]. */
+int b200_rmsnorm_silu_cl(const void* x, void* y, const void* gamma, int64_t pixels, int C, int silu, void* stream);
+
+/* Nearest-exact 2x spatial upsample (WanUpsample :226-237): [T,H,W,C] -> [T,2H,2W,C]. */
+int b200_upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, void* stream);
+
+/* P = softmax(S * scale) row-wise; S fp32 [rows, cols] (row stride lds), P bf16 (row stride ldp).  Mid-block
+ * single-head attention (WanAttentionBlock :461-490), whose head dim (= channels) is not 128. */
+int b200_softmax_rows(const float* s, void* p, int rows, int cols, int64_t lds, int64_t ldp, float scale, void* stream);
+
+/* Blend a decoded tile (planar bf16 [planes, th, tw], planes = 3*T) with its upper / left neighbours, in place, in
+ * the reference's order and bf16 arithmetic (blend_v then blend_h, :1404-1422), then write the cropped, clamped
+ * [-1,1] tile into the frame buffer [planes, OH, OW] at (y0, x0) (:1600-1619). */
+int b200_blend_tile(void* tile, const void* up, const void* left, void* frame, int planes, int th, int tw, int up_h,
+                    int up_w, int left_h, int left_w, int blend, int crop_h, int crop_w, int y0, int x0, int OH, int OW,
+                    void* stream);
 
 #ifdef __cplusplus
 }

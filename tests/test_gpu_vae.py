@@ -1,0 +1,176 @@
+"""GPU parity tests of the Wan VAE decode path (C ABI: b200_conv3d_cl, b200_rmsnorm_silu_cl, b200_upsample2x_cl,
+b200_softmax_rows, b200_blend_tile, b200_linear) against oracle/wan_vae.py and the golden vectors recorded from the
+reference's AutoencoderKLWan.
+
+Tolerances: convolutions -- relative L2 <= 4e-3 vs fp32 math on the same bf16 operands (one bf16 output rounding);
+copy-like kernels (upsample, blend) -- exact; whole decode -- relative L2 vs the fp32 oracle <= max(1e-2, 1.5 x the
+reference's own bf16 error vs that oracle) and relative L2 <= 3e-2 vs the reference's bf16 output.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import wan_vae
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _cl(x):  # [1,C,T,H,W] -> channels-last [T,H,W,C] bf16 on the GPU
+    return x[0].permute(1, 2, 3, 0).contiguous().to(DEV, torch.bfloat16)
+
+
+def _tap_major(w):
+    from apex_studio_b200.vae.wan import AutoencoderKLWan
+
+    return AutoencoderKLWan._tap_major(w).to(DEV, torch.bfloat16)
+
+
+@pytest.mark.parametrize("T,H,W,cin,cout,taps", [
+    (3, 8, 8, 32, 32, (3, 3, 3)),       # BK=32 path (SWIZZLE_64B), tiny
+    (2, 12, 28, 64, 96, (3, 3, 3)),     # ragged W (28 -> BW 16), BK=64
+    (5, 18, 16, 96, 96, (3, 3, 3)),     # Cin 96 = 3 chunks of 32
+    (4, 9, 5, 128, 384, (3, 3, 3)),     # tiny W, two N tiles of 192
+    (3, 32, 32, 384, 384, (3, 3, 3)),   # production first-stage shape
+    (2, 40, 136, 192, 96, (1, 3, 3)),   # per-frame Conv2d of WanResample, W > 128
+    (6, 6, 10, 64, 128, (3, 1, 1)),     # time_conv taps
+])
+def test_conv3d_vs_torch(T, H, W, cin, cout, taps):
+    from apex_studio_b200.vae.wan import conv3d_cl
+
+    g = torch.Generator().manual_seed(T * 100 + H + W + cin)
+    x = torch.randn(1, cin, T, H, W, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, *taps, generator=g) * (cin * taps[0] * taps[1] * taps[2]) ** -0.5).bfloat16()
+    b = (torch.randn(cout, generator=g) * 0.1).bfloat16()
+    ref = wan_vae.causal_conv3d(x.float(), {"c.weight": w.float(), "c.bias": b.float()}, "c")   # fp32 math
+    out = conv3d_cl(_cl(x), _tap_major(w.float()), b.to(DEV), taps, cout)
+    got = out.permute(3, 0, 1, 2).unsqueeze(0)
+    assert rel_l2(got, ref) <= 4e-3
+    # residual epilogue
+    res = torch.randn(1, cout, T, H, W, generator=g).bfloat16()
+    out2 = conv3d_cl(_cl(x), _tap_major(w.float()), b.to(DEV), taps, cout, residual=_cl(res))
+    assert rel_l2(out2.permute(3, 0, 1, 2).unsqueeze(0), ref + res.float()) <= 4e-3
+
+
+def test_conv3d_planar_and_interleave_outputs():
+    from apex_studio_b200.vae.wan import conv3d_cl
+
+    g = torch.Generator().manual_seed(5)
+    T, H, W, C = 4, 10, 12, 64
+    x = torch.randn(1, C, T, H, W, generator=g).bfloat16()
+    # conv_out: 3 real channels padded to 16, planar output
+    w = (torch.randn(3, C, 3, 3, 3, generator=g) * (27 * C) ** -0.5).bfloat16()
+    b = (torch.randn(3, generator=g) * 0.1).bfloat16()
+    ref = wan_vae.causal_conv3d(x.float(), {"c.weight": w.float(), "c.bias": b.float()}, "c")[0]
+    wp = F.pad(w.float(), (0, 0, 0, 0, 0, 0, 0, 0, 0, 13))
+    out = conv3d_cl(_cl(x), _tap_major(wp), F.pad(b, (0, 13)).to(DEV), (3, 3, 3), 16, planar_channels=3)
+    assert out.shape == (3, T, H, W) and rel_l2(out, ref) <= 4e-3
+    # time_conv + 2x temporal interleave (upsample3d): frame 0 bypasses, frames 1.. doubled
+    wt = (torch.randn(2 * C, C, 3, 1, 1, generator=g) * (3 * C) ** -0.5).bfloat16()
+    bt = (torch.randn(2 * C, generator=g) * 0.1).bfloat16()
+    rest = wan_vae.causal_conv3d(x[:, :, 1:].float(), {"c.weight": wt.float(), "c.bias": bt.float()}, "c")
+    rest = rest.reshape(1, 2, C, T - 1, H, W)
+    expect = torch.cat([x[:, :, :1].float(), torch.stack((rest[:, 0], rest[:, 1]), 3).reshape(1, C, 2 * (T - 1), H, W)], 2)
+    xcl = _cl(x)
+    y = torch.empty(1 + 2 * (T - 1), H, W, C, device=DEV, dtype=torch.bfloat16)
+    y[0].copy_(xcl[0])
+    conv3d_cl(xcl[1:], _tap_major(wt.float()), bt.to(DEV), (3, 1, 1), 2 * C, out=y, interleave=True)
+    assert rel_l2(y.permute(3, 0, 1, 2).unsqueeze(0), expect) <= 4e-3
+
+
+@pytest.mark.parametrize("C", [32, 96, 192, 384])
+def test_rmsnorm_silu_and_upsample(C):
+    from apex_studio_b200.vae.wan import rmsnorm_silu_cl, upsample2x_cl
+
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(1, C, 3, 7, 9, generator=g).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).bfloat16()
+    ref = F.silu(wan_vae.rms_norm(x.float(), gamma.float().view(C, 1, 1, 1)))
+    out = rmsnorm_silu_cl(_cl(x), gamma.to(DEV)).permute(3, 0, 1, 2).unsqueeze(0)
+    assert rel_l2(out, ref) <= 3e-3
+    ref2 = wan_vae.rms_norm(x.float(), gamma.float().view(C, 1, 1, 1))
+    out2 = rmsnorm_silu_cl(_cl(x), gamma.to(DEV), silu=False).permute(3, 0, 1, 2).unsqueeze(0)
+    assert rel_l2(out2, ref2) <= 3e-3
+    up = upsample2x_cl(_cl(x)).permute(3, 0, 1, 2)                                   # [C,T,2H,2W]
+    exp = F.interpolate(x[0].permute(1, 0, 2, 3).float(), scale_factor=(2.0, 2.0), mode="nearest-exact").permute(1, 0, 2, 3)
+    assert torch.equal(up.float().cpu(), exp)
+
+
+def test_softmax_rows_and_mid_attention():
+    from apex_studio_b200.vae.wan import AutoencoderKLWan, WanVAEConfig, softmax_rows
+
+    s = torch.randn(300, 520, device=DEV) * 4
+    p = softmax_rows(s, 0.37)
+    assert rel_l2(p, torch.softmax(s * 0.37, dim=-1)) <= 3e-3
+    # whole attention block vs oracle
+    C, T, H, W = 128, 2, 8, 12
+    w = wan_vae.make_weights(base_dim=32, seed=7)
+    vae = AutoencoderKLWan(WanVAEConfig(base_dim=32))
+    vae.load_state_dict(w, device=DEV)
+    x = torch.randn(1, C, T, H, W, generator=torch.Generator().manual_seed(2)).bfloat16()
+    ref = wan_vae.attn_block(x.float(), w, "decoder.mid_block.attentions.0")
+    out = vae._attn_block(_cl(x), "decoder.mid_block.attentions.0").permute(3, 0, 1, 2).unsqueeze(0)
+    assert rel_l2(out, ref) <= 5e-3
+
+
+def test_blend_tile_matches_reference_order():
+    """2x2 tiles through b200_blend_tile vs the oracle's in-place blend/crop/clamp on the same bf16 tiles."""
+    from apex_studio_b200.vae.wan import blend_tile
+
+    g = torch.Generator().manual_seed(3)
+    T, th, tw, stride, blend = 2, 32, 32, 24, 8
+    shapes = [[(32, 32), (32, 20)], [(18, 32), (18, 20)]]
+    tiles = [[(torch.randn(1, 3, T, h, w, generator=g) * 0.8).bfloat16() for (h, w) in row] for row in shapes]
+    # oracle (bf16 tensors, in place, reference order)
+    rows = [[t.clone() for t in row] for row in tiles]
+    out_rows = []
+    for i, row in enumerate(rows):
+        res = []
+        for j, tile in enumerate(row):
+            if i > 0:
+                tile = wan_vae._blend_v(rows[i - 1][j], tile, blend)
+            if j > 0:
+                tile = wan_vae._blend_h(row[j - 1], tile, blend)
+            res.append(tile[:, :, :, :stride, :stride])
+        out_rows.append(torch.cat(res, dim=-1))
+    OH, OW = 24 + 18, 24 + 20
+    expect = torch.clamp(torch.cat(out_rows, dim=3)[:, :, :, :OH, :OW], -1.0, 1.0)[0]
+    dev_tiles = [[t[0].to(DEV).contiguous() for t in row] for row in tiles]
+    frame = torch.zeros(3, T, OH, OW, device=DEV, dtype=torch.bfloat16)
+    for i in range(2):
+        for j in range(2):
+            blend_tile(dev_tiles[i][j], dev_tiles[i - 1][j] if i > 0 else None, dev_tiles[i][j - 1] if j > 0 else None,
+                       frame, blend, stride, i * stride, j * stride)
+    assert torch.equal(frame.cpu(), expect)
+
+
+@pytest.mark.parametrize("name,tiling,sub", [("untiled", False, 2), ("tiled", True, 3)])
+def test_vae_decode_vs_reference_golden(name, tiling, sub):
+    from apex_studio_b200.vae import AutoencoderKLWan, WanVAEConfig
+
+    gold = np.load(os.path.join(GOLDEN, "wan_vae.npz"))
+    w = wan_vae.make_weights(base_dim=32, seed=7)
+    vae = AutoencoderKLWan(WanVAEConfig(base_dim=32))
+    vae.load_state_dict(w, device=DEV)
+    lat = torch.from_numpy(gold[name + "_latents"])
+    z = vae.denormalize_latents(lat).to(torch.bfloat16)         # base_engine.py:2040-2048
+    if tiling:
+        vae.enable_tiling()
+    out = vae.decode(z.to(DEV), return_dict=False)[0]
+    assert list(out.shape) == gold[name + "_shape"].tolist() and out.dtype == torch.bfloat16
+    assert out.abs().max().item() <= 1.0
+    got = out[..., ::sub, ::sub]
+    exact = torch.from_numpy(gold[name + "_out_fp32"])           # reference, fp32
+    ref16 = torch.from_numpy(gold[name + "_out_bf16"])           # reference, bf16 pipeline on CPU
+    ref_err, our_err = rel_l2(ref16, exact), rel_l2(got, exact)
+    assert our_err <= max(1e-2, 1.5 * ref_err), (our_err, ref_err)
+    assert rel_l2(got, ref16) <= 3e-2
