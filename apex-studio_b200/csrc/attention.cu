@@ -31,6 +31,12 @@ constexpr int KV_SLOTS = 4;
 constexpr int NUM_THREADS = 384;  // warpgroups: softmax0 | softmax1 | {TMA, MMA, 2 idle warps}
 constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+// setmaxnreg budget.  The CTA owns 168 regs x 384 threads = 504 per (softmax0, softmax1, other) warp triple; the
+// increase BLOCKS until the pool has enough registers, so 2 * REGS_SOFTMAX + REGS_OTHER must not exceed 504
+// (216/80 = 512 deadlocked every CTA in bring-up).
+constexpr int REGS_SOFTMAX = 208;
+constexpr int REGS_OTHER = 88;
+static_assert(2 * REGS_SOFTMAX + REGS_OTHER <= 504, "setmaxnreg.inc would wait forever");
 
 struct Params {
   int B, H, Sq, Sk;
@@ -66,8 +72,8 @@ B200_DEVICE float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
-// 2^x for x <= ~9 on the FMA/ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a cubic (max rel err
-// 1.0e-4, far below the bf16 rounding of P), exponent added with an integer shift-add.
+// 2^x for x <= ~9 on the FMA/ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], 2^f by a minimax cubic (max rel err
+// 7.6e-5, far below the bf16 rounding of P), exponent added with an integer shift-add.
 B200_DEVICE float2 exp2_poly2(float2 x) {
   const float magic = 12582912.0f;  // 1.5 * 2^23: adding it rounds x to an integer in the low mantissa bits
   x.x = fmaxf(x.x, -126.0f);
@@ -75,9 +81,10 @@ B200_DEVICE float2 exp2_poly2(float2 x) {
   const float2 t = fadd2(x, make_float2(magic, magic));
   const float2 n = fadd2(t, make_float2(-magic, -magic));
   const float2 f = fadd2(x, make_float2(-n.x, -n.y));
-  float2 p = ffma2(f, make_float2(0.0558263f, 0.0558263f), make_float2(0.2401537f, 0.2401537f));
-  p = ffma2(p, f, make_float2(0.6931472f, 0.6931472f));
-  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  // minimax cubic for 2^f on [-0.5, 0.5]: max relative error 7.6e-5 (bf16 rounding of P is 2e-3)
+  float2 p = ffma2(f, make_float2(0.055205505f, 0.055205505f), make_float2(0.24261397f, 0.24261397f));
+  p = ffma2(p, f, make_float2(0.69325477f, 0.69325477f));
+  p = ffma2(p, f, make_float2(0.9999277f, 0.9999277f));
   float2 r;
   r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
   r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
@@ -137,10 +144,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   // Register budget per SMSP slot is 512 / 3 warps: give the two softmax warpgroups 224 registers each (a whole
   // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 56.
-  // (setmaxnreg sits at the top of each role branch so that ptxas budgets each branch separately.)
-  if (warp == 8) {
+  // (one setmaxnreg per warpgroup, executed by all four of its warps at the same instruction, at the top of the
+  // warpgroup's branch so that ptxas budgets the branch accordingly.)
+  if (warp >= 8) {
+   setmaxnreg_dec<REGS_OTHER>();
+   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    setmaxnreg_dec<80>();
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
       for (int t = 0; t < 2; ++t) {
@@ -165,9 +174,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {
+   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    setmaxnreg_dec<80>();
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ, BKV, 0);  // B = K tile, K-major
       constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ, D, 1);    // B = V tile, MN-major
@@ -241,11 +249,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 10) {
-    setmaxnreg_dec<80>();  // idle warps of the third warpgroup
+   }  // warps 10, 11 of the third warpgroup idle until the final barrier
   } else {
     // ------------------------------------------------------------------ softmax warps
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<REGS_SOFTMAX>();
     const int t = warp >> 2;     // query tile
     const int quad = warp & 3;   // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;

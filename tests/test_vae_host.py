@@ -1,0 +1,56 @@
+"""Host-side logic of the VAE path that needs no GPU: the tap-major weight layout consumed by b200_conv3d_cl,
+channel padding, tile grid, config surface."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import wan_vae
+from apex_studio_b200.vae.wan import AutoencoderKLWan, WanVAEConfig
+
+
+def _implicit_gemm_cpu(x_cl, w_tap, bias, taps, cout):
+    """Pure-torch emulation of what the kernel computes from its operands: for every tap, a shifted window of the
+    channels-last input (zero outside, KT-1 frames of causal left pad) times the tap's [Cout, Cin] matrix."""
+    T, H, W, cin = x_cl.shape
+    kt, kh, kw = taps
+    xp = F.pad(x_cl, (0, 0, kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))
+    y = torch.zeros(T, H, W, cout)
+    w3 = w_tap.view(kt * kh * kw, cout, cin)
+    for a in range(kt):
+        for b in range(kh):
+            for c in range(kw):
+                win = xp[a:a + T, b:b + H, c:c + W]
+                y += win @ w3[(a * kh + b) * kw + c].t()
+    return y + bias
+
+
+@pytest.mark.parametrize("taps", [(3, 3, 3), (1, 3, 3), (3, 1, 1)])
+def test_tap_major_layout_equals_causal_conv(taps):
+    g = torch.Generator().manual_seed(1)
+    cin, cout, T, H, W = 8, 6, 4, 5, 7
+    x = torch.randn(1, cin, T, H, W, generator=g)
+    w = torch.randn(cout, cin, *taps, generator=g)
+    b = torch.randn(cout, generator=g)
+    ref = wan_vae.causal_conv3d(x, {"c.weight": w, "c.bias": b}, "c")[0].permute(1, 2, 3, 0)
+    got = _implicit_gemm_cpu(x[0].permute(1, 2, 3, 0), AutoencoderKLWan._tap_major(w), b, taps, cout)
+    assert torch.allclose(got, ref, atol=1e-4)
+
+
+def test_channel_padding_and_config_surface():
+    w = wan_vae.make_weights(base_dim=32, seed=7)
+    vae = AutoencoderKLWan(WanVAEConfig(base_dim=32))
+    vae.load_state_dict(w, device="cpu")
+    assert vae.w["post_quant_conv.weight"].shape == (32, 16) and vae.w["post_quant_conv.weight"][16:].abs().max() == 0
+    assert vae.w["decoder.conv_in.weight"].shape == (27 * 128, 32)
+    assert vae.w["decoder.conv_in.weight"].view(27, 128, 32)[:, :, 16:].abs().max() == 0
+    assert vae.w["decoder.conv_out.weight"].shape == (27 * 16, 32)
+    assert vae.w["decoder.conv_out.weight"].view(27, 16, 32)[:, 3:].abs().max() == 0
+    assert vae.config.z_dim == 16 and vae.config.scale_factor_spatial == 8 and vae.config.scale_factor_temporal == 4
+    assert vae.dtype == torch.bfloat16 and vae.dims == [128, 128, 128, 64, 32]
+    assert vae.tile_grid(90, 160) == [(i, j) for (i, j, _, _) in wan_vae.tile_grid(90, 160)]
+    lat = torch.randn(1, 16, 2, 4, 4)
+    assert torch.equal(vae.denormalize_latents(lat), wan_vae.denormalize_latents(lat))
+    with pytest.raises(ValueError):
+        AutoencoderKLWan(WanVAEConfig(is_residual=True))
+    with pytest.raises(RuntimeError, match="weights not loaded"):
+        AutoencoderKLWan().decode(torch.zeros(1, 16, 1, 4, 4))
