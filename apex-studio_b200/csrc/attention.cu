@@ -36,6 +36,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 // (216/80 = 512 deadlocked every CTA in bring-up).
 constexpr int REGS_SOFTMAX = 208;
 constexpr int REGS_OTHER = 88;
+constexpr int DEFAULT_VARIANT = 2;
 static_assert(2 * REGS_SOFTMAX + REGS_OTHER <= 504, "setmaxnreg.inc would wait forever");
 
 struct Params {
@@ -108,7 +109,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = kv_empty + KV_SLOTS;  // [2]
   uint64_t* p_full = s_full + 2;           // [2]
   uint64_t* o_done = p_full + 2;           // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* p_half = o_done + 2;           // [2]  VARIANT 3: second half of P (keys 64..127) written
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_half + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -129,6 +131,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);
+      mbar_init(&p_half[t], 4);
       mbar_init(&o_done[t], 1);
     }
     fence_mbar_init();
@@ -191,12 +194,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   make_smem_desc_sw128(b0 + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int t, int slot, bool first) {
+      auto issue_pv_range = [&](int t, int slot, bool first, int kk0, int kk1) {
         const uint32_t b0 = kv_addr + slot * TILE_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
+        for (int kk = kk0; kk < kk1; ++kk) {
           umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
                   make_smem_desc_sw128(b0 + kk * 2048, HALF_BYTES, 1024), idesc_o, (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      // VARIANT 3: the softmax publishes P in two halves (keys 0..63, then 64..127); the first four k-steps of
+      // P V are issued as soon as the first half is in TMEM, overlapping the exps of the second half.
+      auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
+        mbar_wait(&p_full[t], parity);
+        tc_fence_after();
+        if constexpr (VARIANT == 3) {
+          issue_pv_range(t, slot, first, 0, 4);
+          mbar_wait(&p_half[t], parity);
+          tc_fence_after();
+          issue_pv_range(t, slot, first, 4, 8);
+        } else {
+          issue_pv_range(t, slot, first, 0, 8);
         }
       };
       int slot = 0;
@@ -227,9 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (has_next) advance();
 
         mbar_wait(&kv_full[v_slot], v_phase);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, v_slot, j == 0);
+        issue_pv(0, v_slot, j == 0, j & 1);
         umma_commit(&o_done[0]);
         if (has_next) {
           mbar_wait(&kv_full[k_slot], k_phase);
@@ -237,9 +251,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           issue_s(0, k_slot);
           umma_commit(&s_full[0]);
         }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, v_slot, j == 0);
+        issue_pv(1, v_slot, j == 0, j & 1);
         umma_commit(&o_done[1]);
         umma_commit(&kv_empty[v_slot]);
         if (has_next) {
@@ -265,7 +277,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       const int valid = p.Sk - j * BKV;  // >= 128 except possibly for the last tile
-      if constexpr (VARIANT == 2) {
+      if constexpr (VARIANT >= 2) {
         uint32_t s[128];
         tmem_ld_x32(s_addr + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
         tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -326,6 +338,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[k] = pack_bf16x2(e.x, e.y);
           }
           tmem_st_x16(s_addr + c * 16, pk);
+          if (VARIANT == 3 && c == 1) {  // keys 0..63 of P are in TMEM: let the MMA warp start P V
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+          }
         }
         l += sum2.x + sum2.y;
       } else {
@@ -393,7 +411,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (lane == 0) mbar_arrive(VARIANT == 3 ? &p_half[t] : &p_full[t]);
     }
     // epilogue: O / l -> bf16 -> global
     mbar_wait(&o_done[t], (n_kv - 1) & 1);
@@ -469,21 +487,25 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_ss = o_ss;
   p.scale_log2 = scale * 1.4426950408889634f;
 
-  // B200_ATTN_VARIANT=1 selects the two-pass bring-up softmax (A/B measurements); default is variant 2.
+  // B200_ATTN_VARIANT selects the softmax variant for A/B measurements: 1 = two-pass bring-up version,
+  // 2 = single pass + f32x2 + polynomial exp2 offload, 3 = 2 with the split P hand-off.  Default: DEFAULT_VARIANT.
   static int variant = 0;
   if (variant == 0) {
     const char* ev = getenv("B200_ATTN_VARIANT");
-    variant = (ev && ev[0] == '1') ? 1 : 2;
+    variant = (ev && ev[0] >= '1' && ev[0] <= '3') ? (ev[0] - '0') : DEFAULT_VARIANT;
     cudaError_t e1 = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) return B200_ERR_LAUNCH;
+    cudaError_t e3 = cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return B200_ERR_LAUNCH;
   }
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (variant == 1)
     attn_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-  else
+  else if (variant == 2)
     attn_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  else
+    attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

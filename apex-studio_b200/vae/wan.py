@@ -203,6 +203,56 @@ class AutoencoderKLWan:
         self.w = w
         return [], []
 
+    def init_random_weights(self, device="cuda", seed: int = 7):
+        """Synthetic decoder weights in the reference's state-dict format, generated on the device (bench.py; no
+        checkpoints offline): conv weights N(0, 1/fan_in), biases N(0, 0.02^2), gammas 1 + N(0, 0.02^2)."""
+        dev = torch.device(device)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        c = self.config
+        sd: Dict[str, torch.Tensor] = {}
+
+        def conv(name, cout, cin, *k):
+            fan = cin
+            for kk in k:
+                fan *= kk
+            sd[name + ".weight"] = torch.randn(cout, cin, *k, generator=g, device=dev) * fan ** -0.5
+            sd[name + ".bias"] = torch.randn(cout, generator=g, device=dev) * 0.02
+
+        def gamma(name, ch):
+            sd[name] = 1 + torch.randn(ch, generator=g, device=dev) * 0.02
+
+        def res(p, cin, cout):
+            gamma(p + ".norm1.gamma", cin)
+            conv(p + ".conv1", cout, cin, 3, 3, 3)
+            gamma(p + ".norm2.gamma", cout)
+            conv(p + ".conv2", cout, cout, 3, 3, 3)
+            if cin != cout:
+                conv(p + ".conv_shortcut", cout, cin, 1, 1, 1)
+
+        dims = self.dims
+        conv("post_quant_conv", c.z_dim, c.z_dim, 1, 1, 1)
+        conv("decoder.conv_in", dims[0], c.z_dim, 3, 3, 3)
+        res("decoder.mid_block.resnets.0", dims[0], dims[0])
+        gamma("decoder.mid_block.attentions.0.norm.gamma", dims[0])
+        conv("decoder.mid_block.attentions.0.to_qkv", dims[0] * 3, dims[0], 1, 1)
+        conv("decoder.mid_block.attentions.0.proj", dims[0], dims[0], 1, 1)
+        res("decoder.mid_block.resnets.1", dims[0], dims[0])
+        n_up = len(c.dim_mult)
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            cur = cin // 2 if i > 0 else cin
+            for j in range(c.num_res_blocks + 1):
+                res(f"decoder.up_blocks.{i}.resnets.{j}", cur, cout)
+                cur = cout
+            if i != n_up - 1:
+                p = f"decoder.up_blocks.{i}.upsamplers.0"
+                conv(p + ".resample.1", cout // 2, cout, 3, 3)
+                if self.temporal_upsample[i]:
+                    conv(p + ".time_conv", cout * 2, cout, 3, 1, 1)
+        gamma("decoder.norm_out.gamma", dims[-1])
+        conv("decoder.conv_out", c.out_channels, dims[-1], 3, 3, 3)
+        self.load_state_dict(sd, device=dev)
+        return self
+
     # -------------------------------------------------------------------------------- reference API surface
     def enable_tiling(self, tile_sample_min_height=None, tile_sample_min_width=None, tile_sample_stride_height=None,
                       tile_sample_stride_width=None) -> None:

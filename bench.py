@@ -299,6 +299,36 @@ def run_b200_arm(args):
     barrier()
     e2e_ms_step = max_over_ranks(e0.elapsed_time(e1)) / max(e2e_steps, 1)
 
+    # ---- VAE decode of the same latent (second half of the frames/sec metric); tiles dealt over all ranks
+    vae_info = None
+    if not args.no_vae:
+        try:
+            from apex_studio_b200.vae import AutoencoderKLWan
+
+            del high, low, state
+            torch.cuda.empty_cache()
+            vae = AutoencoderKLWan().init_random_weights(dev, seed=7)
+            vae.enable_tiling()
+            zlat = vae.denormalize_latents(torch.randn(LATENT_SHAPE, generator=torch.Generator().manual_seed(42))
+                                           .to(dev)).to(torch.bfloat16)
+            par_v = ParallelContext.create(use_cfg=False) if world > 1 else None
+            l0 = ops.launch_count
+            vae.decode(zlat, parallel=par_v)                      # warm-up (allocator, TMA descriptors, clocks)
+            vae_launches = ops.launch_count - l0
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            frames = vae.decode(zlat, parallel=par_v)[0]
+            v1.record()
+            barrier()
+            vae_ms = max_over_ranks(v0.elapsed_time(v1))
+            vae_info = {"ms": vae_ms, "frames": int(frames.shape[2]), "frames_per_sec": frames.shape[2] / (vae_ms * 1e-3),
+                        "tiles": len(vae.tile_grid(LATENT_SHAPE[3], LATENT_SHAPE[4])), "launches": vae_launches,
+                        "algorithmic_tflops_untiled": 6.39e14 / (vae_ms * 1e-3) / 1e12,
+                        "finite": bool(torch.isfinite(frames.float()).all().item())}
+        except Exception as e:  # the DiT line must survive a VAE problem
+            vae_info = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,6 +368,8 @@ def run_b200_arm(args):
                 "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms_step},
         "gpu_launches": launches, "clocks": clocks,
         "frames_per_sec_50step_denoise_only": 81.0 / (50 * ms_step * 1e-3),
+        "vae_decode": vae_info,
+        "frames_per_sec": (81.0 / (50 * ms_step * 1e-3 + vae_info["ms"] * 1e-3)) if (vae_info and "ms" in vae_info) else None,
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -358,6 +390,7 @@ def main():
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: anything but 40 is labelled REDUCED")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-vae", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
