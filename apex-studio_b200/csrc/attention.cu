@@ -44,6 +44,12 @@ struct Params {
   __nv_bfloat16* o;
   int64_t o_sb, o_sh, o_ss;
   float scale_log2;
+  // Sequence-parallel "heads -> tokens" exchange fused into the epilogue: query row r belongs to the rank that owns
+  // token r, so its output row is stored straight into that peer's [S/P, H_total*128] buffer over NVLink.
+  void* o_peer[8];
+  int n_peers;        // 0 = plain store into `o`
+  int rows_per_rank;  // S / P
+  int head_off;       // first global head computed by this rank
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -419,6 +425,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float inv_l = 1.0f / l;
     const int row = q_block * (2 * BQ) + t * BQ + quad * 32 + lane;
     __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
+    if (p.n_peers > 0 && row < p.Sq) {
+      const int d = row / p.rows_per_rank;
+      orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
+             static_cast<int64_t>(head + p.head_off) * p.o_sh;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t r[32];
@@ -449,10 +460,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace attn
 }  // namespace b200
 
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                         int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                         int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream);
+
 extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                              int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                              int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                              float scale, void* stream) {
+  return attn_fwd_impl(q, k, v, o, B, H, Sq, Sk, D, q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss, o_sb, o_sh, o_ss,
+                       scale, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D,
+                                     int64_t q_sh, int64_t q_ss, int64_t k_sh, int64_t k_ss, int64_t v_sh, int64_t v_ss,
+                                     void* const* o_peers, int n_peers, int rows_per_rank, int head_off, int64_t o_sh,
+                                     int64_t o_ss, float scale, void* stream) {
+  if (!o_peers || n_peers < 1 || n_peers > 8 || rows_per_rank <= 0) return B200_ERR_ARG;
+  if (static_cast<int64_t>(rows_per_rank) * n_peers < Sq) return B200_ERR_SHAPE;
+  for (int i = 0; i < n_peers; ++i)
+    if (!o_peers[i] || (reinterpret_cast<uintptr_t>(o_peers[i]) & 15)) return B200_ERR_ALIGN;
+  return attn_fwd_impl(q, k, v, o_peers[0], 1, H, Sq, Sk, D, 0, q_sh, q_ss, 0, k_sh, k_ss, 0, v_sh, v_ss, 0, o_sh, o_ss,
+                       scale, o_peers, n_peers, rows_per_rank, head_off, stream);
+}
+
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                         int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                         int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream) {
   using namespace b200;
   using namespace b200::attn;
   if (!q || !k || !v || !o) return B200_ERR_ARG;
@@ -486,6 +522,10 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_ss = o_ss;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.n_peers = n_peers;
+  p.rows_per_rank = rows_per_rank;
+  p.head_off = head_off;
+  for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
 
   // B200_ATTN_VARIANT selects the softmax variant for A/B measurements: 1 = two-pass bring-up version,
   // 2 = single pass + f32x2 + polynomial exp2 offload, 3 = 2 with the split P hand-off.  Default: DEFAULT_VARIANT.

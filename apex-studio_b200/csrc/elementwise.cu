@@ -128,10 +128,22 @@ layernorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __
 // reference: InplaceRMSNorm (mod.py:24-35), apply_wan_rope_inplace (ops.py:101-160)
 // rope table: bf16 [rows, head_dim] = (cos0, sin0, cos1, sin1, ...) already cast to bf16 as the reference does.
 // ------------------------------------------------------------------------------------------------
+// Scatter mode (sequence-parallel "tokens -> heads" exchange fused into this kernel): instead of updating x in
+// place, channel chunk c of token `row` is stored straight into the peer GPU that owns its head group, over
+// NVLink peer memory: dst = peer[ch / width] + elem_off + (row0 + row) * width + ch % width.
+struct PeerScatter {
+  void* peer[8];
+  int n_peers;        // 0 = in place
+  int width;          // channels per peer = (heads / P) * head_dim
+  int row0;           // first global token of this rank's shard
+  int64_t elem_off;   // element offset of the q / k / v plane inside each peer's receive buffer
+};
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                    const __nv_bfloat16* __restrict__ rope, int dim, int head_dim, int64_t ldx, float eps) {
+                    const __nv_bfloat16* __restrict__ rope, int dim, int head_dim, int64_t ldx, float eps,
+                    const PeerScatter sc) {
   __shared__ float red[THREADS / 32];
   const int64_t row = blockIdx.x;
   uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
@@ -186,7 +198,15 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
           f[2 * j + 1] = round_bf16(im * co) + re * si;
         }
       }
-      xr[c] = pack8(f);
+      if (sc.n_peers == 0) {
+        xr[c] = pack8(f);
+      } else {
+        const int ch = c << 3;
+        const int d = ch / sc.width;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sc.peer[d]) + sc.elem_off +
+                             (static_cast<int64_t>(sc.row0) + row) * sc.width + (ch - d * sc.width);
+        *reinterpret_cast<uint4*>(dst) = pack8(f);
+      }
     }
   }
 }
@@ -278,8 +298,8 @@ extern "C" int b200_layernorm_modulate(const void* x, void* y, const void* scale
   return B200_OK;
 }
 
-extern "C" int b200_rmsnorm_rope(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
-                                 int64_t ldx, float eps, void* stream) {
+static int rmsnorm_rope_launch(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
+                               int64_t ldx, float eps, const PeerScatter& sc, void* stream) {
   if (!x) return B200_ERR_ARG;
   if (rows <= 0 || heads <= 0 || head_dim <= 0) return B200_ERR_SHAPE;
   if ((head_dim % 8) || (ldx % 8)) return B200_ERR_ALIGN;
@@ -289,12 +309,36 @@ extern "C" int b200_rmsnorm_rope(void* x, const void* w, const void* rope, int r
   int rc = dispatch_threads(dim / 8, [&](auto T) {
     constexpr int THREADS = decltype(T)::value;
     rmsnorm_rope_kernel<THREADS><<<rows, THREADS, 0, st>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                           (const __nv_bfloat16*)rope, dim, head_dim, ldx, eps);
+                                                           (const __nv_bfloat16*)rope, dim, head_dim, ldx, eps, sc);
     return B200_OK;
   });
   if (rc) return rc;
   B200_CHECK_LAUNCH();
   return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_rope(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
+                                 int64_t ldx, float eps, void* stream) {
+  PeerScatter sc;
+  sc.n_peers = 0;
+  return rmsnorm_rope_launch(x, w, rope, rows, heads, head_dim, ldx, eps, sc, stream);
+}
+
+extern "C" int b200_rmsnorm_rope_scatter(const void* x, const void* w, const void* rope, int rows, int heads,
+                                         int head_dim, int64_t ldx, float eps, void* const* peers, int n_peers,
+                                         int64_t dst_elem_offset, int row0, void* stream) {
+  if (!peers || n_peers < 1 || n_peers > 8 || (heads % n_peers)) return B200_ERR_ARG;
+  PeerScatter sc;
+  sc.n_peers = n_peers;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peers[i] || !aligned16(peers[i])) return B200_ERR_ALIGN;
+    sc.peer[i] = peers[i];
+  }
+  sc.width = (heads / n_peers) * head_dim;
+  sc.row0 = row0;
+  sc.elem_off = dst_elem_offset;
+  if (dst_elem_offset % 8) return B200_ERR_ALIGN;
+  return rmsnorm_rope_launch(const_cast<void*>(x), w, rope, rows, heads, head_dim, ldx, eps, sc, stream);
 }
 
 extern "C" int b200_gate_residual(void* h, const void* y, const void* gate, int rows, int dim, int64_t ldh, int64_t ldy,

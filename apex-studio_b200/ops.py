@@ -198,6 +198,40 @@ def rmsnorm_rope_(x: torch.Tensor, weight: Optional[torch.Tensor], rope: Optiona
     return x
 
 
+def rmsnorm_rope_scatter(x: torch.Tensor, weight: Optional[torch.Tensor], rope: Optional[torch.Tensor], heads: int,
+                         eps: float, peers, n_peers: int, dst_elem_offset: int, row0: int, *, norm: bool = True) -> None:
+    """rmsnorm_rope_ whose result is stored into the peer GPUs' receive planes (tokens -> heads exchange fused into
+    the kernel); ``peers`` is a ctypes array of ``n_peers`` device pointers (parallel.PeerExchange)."""
+    _require_cuda_bf16("x", x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [rows, dim] with a contiguous last dim")
+    rows, dim = x.shape
+    lib = _lib.load()
+    rc = lib.b200_rmsnorm_rope_scatter(x.data_ptr(), _ptr(weight), _ptr(rope), rows, heads, dim // heads, x.stride(0),
+                                       float(eps) if norm else -1.0, peers, n_peers, dst_elem_offset, row0, _stream())
+    _lib.check(rc, "b200_rmsnorm_rope_scatter")
+    _count()
+
+
+def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_peers, n_peers: int, rows_per_rank: int,
+                      head_off: int, o_row_stride: int, softmax_scale: Optional[float] = None) -> None:
+    """attention for q/k/v [1,H,S,128] whose output rows are stored into the token-owning peers' [S/P, H_total*128]
+    buffers (heads -> tokens exchange fused into the attention epilogue)."""
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _require_cuda_bf16(name, t)
+    B, H, Sq, D = q.shape
+    Sk = k.shape[2]
+    if B != 1 or D != 128:
+        raise ValueError("attention_scatter needs batch 1 and head_dim 128")
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lib = _lib.load()
+    rc = lib.b200_attn_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), H, Sq, Sk, D, q.stride(1), q.stride(2),
+                                   k.stride(1), k.stride(2), v.stride(1), v.stride(2), o_peers, n_peers, rows_per_rank,
+                                   head_off, D, o_row_stride, scale, _stream())
+    _lib.check(rc, "b200_attn_fwd_scatter")
+    _count()
+
+
 def gate_residual_(h: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor] = None) -> torch.Tensor:
     """In place: h += y * gate (gate [dim] or None)."""
     _require_cuda_bf16("h", h)

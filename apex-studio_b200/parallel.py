@@ -37,6 +37,18 @@ class ParallelContext:
     cfg_group: Optional[object] = None   # process group of my CFG pair
     sp_group: Optional[object] = None    # process group of my token-shard peers
     world_group: Optional[object] = None
+    #: fuse the Ulysses exchange into the kernels over NVLink peer memory (PeerExchange) instead of NCCL all-to-all
+    use_p2p: bool = False
+    _p2p: Optional[dict] = None
+
+    def peer_exchange(self, tokens_total: int, heads: int, head_dim: int, device) -> "PeerExchange":
+        """Symmetric buffers for one (tokens, heads) shape; allocated and rendezvoused once (collective!)."""
+        if self._p2p is None:
+            self._p2p = {}
+        key = (tokens_total, heads, head_dim)
+        if key not in self._p2p:
+            self._p2p[key] = PeerExchange(self, tokens_total, heads, head_dim, device)
+        return self._p2p[key]
 
     # ------------------------------------------------------------------------------------ construction
     @classmethod
@@ -44,7 +56,7 @@ class ParallelContext:
         return cls()
 
     @classmethod
-    def create(cls, use_cfg: bool = True, world_group=None) -> "ParallelContext":
+    def create(cls, use_cfg: bool = True, world_group=None, use_p2p: bool = False) -> "ParallelContext":
         """Build the cfg x sp layout for the initialised default process group.  Every rank must call this
         (``dist.new_group`` is collective)."""
         if not dist.is_available() or not dist.is_initialized():
@@ -64,7 +76,7 @@ class ParallelContext:
             if rank in ranks:
                 cfg_group = g
         return cls(rank=rank, world_size=world, cfg_size=cfg_size, sp_size=sp_size, cfg_group=cfg_group,
-                   sp_group=sp_group, world_group=world_group)
+                   sp_group=sp_group, world_group=world_group, use_p2p=use_p2p)
 
     @property
     def cfg_rank(self) -> int:
@@ -135,6 +147,43 @@ class ParallelContext:
         if self.world_size == 1:
             return mine.unsqueeze(0)
         return _all_gather_stacked(mine, self.world_size, self.world_group)
+
+
+class PeerExchange:
+    """NVLink peer-mapped (symmetric) buffers for the Ulysses exchange FUSED into the kernels: the q/k RMS-norm+RoPE
+    kernel and a scatter copy of v store straight into the receive planes ``qkv[3, S, (H/P)*Dh]`` of the rank that
+    owns each head group (``b200_rmsnorm_rope_scatter``), and the attention epilogue stores each output row into the
+    ``o[S/P, H*Dh]`` buffer of the rank that owns the token (``b200_attn_fwd_scatter``).  No packing pass, no NCCL
+    all-to-all; two device-side barriers per layer order the stores against their consumers.
+
+    Built on ``torch.distributed._symmetric_memory`` (CUDA peer mappings + signal-pad barriers)."""
+
+    def __init__(self, par: "ParallelContext", tokens_total: int, heads: int, head_dim: int, device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        P = par.sp_size
+        if heads % P or tokens_total % P:
+            raise ValueError("heads and tokens must be divisible by the sequence-parallel size")
+        self.P, self.width, self.n_local = P, (heads // P) * head_dim, tokens_total // P
+        self.tokens_total, self.plane = tokens_total, tokens_total * (heads // P) * head_dim
+        self.head_off = par.sp_rank * (heads // P)
+        self.row0 = par.sp_rank * self.n_local
+        try:  # needed by older torch releases, a no-op / absent in newer ones
+            symm_mem.enable_symm_mem_for_group(par.sp_group.group_name)
+        except Exception:
+            pass
+        self.qkv = symm_mem.empty((3, tokens_total, self.width), dtype=torch.bfloat16, device=device)
+        self.o = symm_mem.empty((self.n_local, heads * head_dim), dtype=torch.bfloat16, device=device)
+        self.h_qkv = symm_mem.rendezvous(self.qkv, par.sp_group)
+        self.h_o = symm_mem.rendezvous(self.o, par.sp_group)
+        self.qkv_peers = (ctypes.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
+        self.o_peers = (ctypes.c_void_p * P)(*[int(p) for p in self.h_o.buffer_ptrs])
+
+    def barrier(self, channel: int) -> None:
+        """Device-side barrier over the sp group on the current stream (all earlier peer stores are visible after it)."""
+        self.h_qkv.barrier(channel=channel)
 
 
 def _all_gather_stacked(mine: torch.Tensor, n: int, group) -> torch.Tensor:

@@ -183,7 +183,8 @@ class AutoencoderKLWan:
                 continue
             v = v.detach().to(dev, torch.float32)
             if k == "post_quant_conv.weight":
-                w[k] = torch.nn.functional.pad(v.reshape(z, z), (0, 0, 0, zp - z)).to(bf).contiguous()   # [zp, z]
+                # [zp, 64]: output channels padded to zp (zeros), input channels padded to one 64-wide K tile
+                w[k] = torch.nn.functional.pad(v.reshape(z, z), (0, 64 - z, 0, zp - z)).to(bf).contiguous()
             elif k == "post_quant_conv.bias":
                 w[k] = torch.nn.functional.pad(v, (0, zp - z)).to(bf).contiguous()
             elif k == "decoder.conv_in.weight":
@@ -326,8 +327,9 @@ class AutoencoderKLWan:
         """z [zc, T, h, w] (one latent tile, all frames) -> planar bf16 [3, 1+4(T-1), 8h, 8w] (pre-clamp)."""
         w = self.w
         zc, T, h, wd = z.shape
-        x = z.permute(1, 2, 3, 0).to(torch.bfloat16).contiguous()                          # [T,h,w,zc]
-        x = ops.linear(x.view(-1, zc), w["post_quant_conv.weight"], w["post_quant_conv.bias"]).view(T, h, wd, self.z_pad)
+        x = torch.zeros(T, h, wd, 64, dtype=torch.bfloat16, device=z.device)               # K padded to one tile
+        x[..., :zc] = z.permute(1, 2, 3, 0)
+        x = ops.linear(x.view(-1, 64), w["post_quant_conv.weight"], w["post_quant_conv.bias"]).view(T, h, wd, self.z_pad)
         x = conv3d_cl(x, w["decoder.conv_in.weight"], w["decoder.conv_in.bias"], (3, 3, 3), self.dims[0])
         x = self._res_block(x, "decoder.mid_block.resnets.0")
         x = self._attn_block(x, "decoder.mid_block.attentions.0")

@@ -240,10 +240,28 @@ class WanTransformer3DModel:
         ops.layernorm_modulate(h, scale_msa, shift_msa, eps=eps, out=ws.norm)
         ops.linear(ws.norm, w[p + ".attn1.to_qkv.weight"], w[p + ".attn1.to_qkv.bias"], out=ws.qkv)
         q, k, v = ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:]
-        ops.rmsnorm_rope_(q, w[p + ".attn1.norm_q.weight"], rope, heads, eps)
-        ops.rmsnorm_rope_(k, w[p + ".attn1.norm_k.weight"], rope, heads, eps)
         as4 = lambda t, n: t.view(1, n, -1, hd).transpose(1, 2)  # [1,H,n,hd] strided view
-        if par is None or par.sp_size == 1:
+        attn_out = ws.attn
+        if par is not None and par.sp_size > 1 and par.use_p2p:
+            # Ulysses exchange fused into the kernels over NVLink peer memory (parallel.PeerExchange):
+            # norm+RoPE(q,k) and a copy of v store straight into the head-owner's planes, the attention epilogue
+            # stores straight into the token-owner's [S/P, dim] buffer; two device-side barriers per layer.
+            ex = par.peer_exchange(S * par.sp_size, heads, hd, h.device)
+            ops.rmsnorm_rope_scatter(q, w[p + ".attn1.norm_q.weight"], rope, heads, eps, ex.qkv_peers, ex.P, 0, ex.row0)
+            ops.rmsnorm_rope_scatter(k, w[p + ".attn1.norm_k.weight"], rope, heads, eps, ex.qkv_peers, ex.P, ex.plane,
+                                     ex.row0)
+            ops.rmsnorm_rope_scatter(v, None, None, heads, eps, ex.qkv_peers, ex.P, 2 * ex.plane, ex.row0, norm=False)
+            ex.barrier(0)
+            ops.attention_scatter(as4(ex.qkv[0], ex.tokens_total), as4(ex.qkv[1], ex.tokens_total),
+                                  as4(ex.qkv[2], ex.tokens_total), ex.o_peers, ex.P, ex.n_local, ex.head_off, d)
+            ex.barrier(1)
+            attn_out = ex.o
+        else:
+            ops.rmsnorm_rope_(q, w[p + ".attn1.norm_q.weight"], rope, heads, eps)
+            ops.rmsnorm_rope_(k, w[p + ".attn1.norm_k.weight"], rope, heads, eps)
+        if par is not None and par.sp_size > 1 and par.use_p2p:
+            pass
+        elif par is None or par.sp_size == 1:
             ops.attention(as4(q, S), as4(k, S), as4(v, S), out=as4(ws.attn, S))
         else:
             # Ulysses: tokens -> heads, global attention over my heads, heads -> tokens
@@ -253,7 +271,7 @@ class WanTransformer3DModel:
             ops.attention(as4(qkv_h[0], S_total), as4(qkv_h[1], S_total), as4(qkv_h[2], S_total),
                           out=as4(o_h, S_total))
             par.heads_to_tokens(o_h, out=ws.attn)
-        ops.linear(ws.attn, w[p + ".attn1.to_out.0.weight"], w[p + ".attn1.to_out.0.bias"],
+        ops.linear(attn_out, w[p + ".attn1.to_out.0.weight"], w[p + ".attn1.to_out.0.bias"],
                    epilogue=ops.EPI_GATE_RES, out=h, gate=gate_msa)
 
         # 2. cross-attention (K/V from the text context, no RoPE)

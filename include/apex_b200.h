@@ -112,6 +112,33 @@ int b200_gate_residual(void* h, const void* y, const void* gate, int rows, int d
 int b200_cfg_combine(const void* cond, const void* uncond, void* out, float guidance, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Sequence-parallel exchange fused into the kernels (no reference counterpart: the reference runs one job on one
+ * GPU).  `peers[i]` are device pointers to rank i's receive buffer, mapped into this process
+ * over NVLink (CUDA peer / symmetric memory); stores go straight to the owning GPU, so the all-to-all of the Ulysses
+ * layout overlaps the arithmetic tile by tile and no pack / NCCL step remains.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/*
+ * b200_rmsnorm_rope with the "tokens -> heads" scatter: channel c of local token r is written to
+ *   peers[c / width] + dst_elem_offset + (row0 + r) * width + c % width,   width = (heads / n_peers) * head_dim,
+ * i.e. into the [S_total, width] plane (q, k or v -- selected by dst_elem_offset) of the rank that owns that head
+ * group.  x is not modified.  eps < 0 and rope == NULL make it a pure scatter copy (used for v).
+ */
+int b200_rmsnorm_rope_scatter(const void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
+                              int64_t ldx, float eps, void* const* peers, int n_peers, int64_t dst_elem_offset,
+                              int row0, void* stream);
+
+/*
+ * b200_attn_fwd (batch 1) with the "heads -> tokens" scatter: this rank computes heads [head_off, head_off + H) for
+ * ALL Sq query rows; output row r is written to o_peers[r / rows_per_rank] at row r % rows_per_rank, head
+ * head_off + h of that rank's [rows_per_rank, H_total * 128] buffer (row stride o_ss, head stride o_sh).
+ */
+int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D, int64_t q_sh,
+                          int64_t q_ss, int64_t k_sh, int64_t k_ss, int64_t v_sh, int64_t v_ss, void* const* o_peers,
+                          int n_peers, int rows_per_rank, int head_off, int64_t o_sh, int64_t o_ss, float scale,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Wan 3D-VAE decode (AutoencoderKLWan.decode, vae/wan/model.py:1378; BaseEngine.vae_decode, engine/base_engine.py:2030).
  * Activations are channels-last bf16 [T, H, W, C] (one spatial tile of one video at a time).
  * --------------------------------------------------------------------------------------------------------- */

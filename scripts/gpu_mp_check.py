@@ -52,6 +52,18 @@ def main():
     res["sp_layout"] = [par_sp.cfg_size, par_sp.sp_size]
     res["sp_max_abs_diff"] = (single.float() - sharded.float()).abs().max().item()
 
+    # 1b. the same with the exchange fused into the kernels over NVLink peer memory
+    try:
+        par_p2p = ParallelContext.create(use_cfg=False, use_p2p=True)
+        fused = model(lat.to(dev, torch.bfloat16), t, text.to(dev), return_dict=False, parallel=par_p2p)[0]
+        fused2 = model(lat.to(dev, torch.bfloat16), t, text.to(dev), return_dict=False, parallel=par_p2p)[0]
+        res["p2p_max_abs_diff"] = (single.float() - fused.float()).abs().max().item()
+        res["p2p_repeat_max_abs_diff"] = (fused2.float() - fused.float()).abs().max().item()
+    except Exception as e:  # noqa
+        import traceback
+
+        res["p2p_error"] = repr(e)[:300] + " | " + traceback.format_exc()[-600:]
+
     # 2. CFG x SP denoise loop
     par = ParallelContext.create(use_cfg=True)
 

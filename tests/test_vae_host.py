@@ -40,7 +40,8 @@ def test_channel_padding_and_config_surface():
     w = wan_vae.make_weights(base_dim=32, seed=7)
     vae = AutoencoderKLWan(WanVAEConfig(base_dim=32))
     vae.load_state_dict(w, device="cpu")
-    assert vae.w["post_quant_conv.weight"].shape == (32, 16) and vae.w["post_quant_conv.weight"][16:].abs().max() == 0
+    pq = vae.w["post_quant_conv.weight"]
+    assert pq.shape == (32, 64) and pq[16:].abs().max() == 0 and pq[:, 16:].abs().max() == 0
     assert vae.w["decoder.conv_in.weight"].shape == (27 * 128, 32)
     assert vae.w["decoder.conv_in.weight"].view(27, 128, 32)[:, :, 16:].abs().max() == 0
     assert vae.w["decoder.conv_out.weight"].shape == (27 * 16, 32)
