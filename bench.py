@@ -190,7 +190,9 @@ def run_b200_arm(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    par = ParallelContext.create(use_cfg=True) if world > 1 else ParallelContext.single()
+    # B200_P2P=1: Ulysses exchange fused into the kernels over NVLink peer memory instead of NCCL all-to-all
+    use_p2p = os.environ.get("B200_P2P", "0") == "1"
+    par = ParallelContext.create(use_cfg=True, use_p2p=use_p2p) if world > 1 else ParallelContext.single()
 
     cfg = WanConfig(num_layers=args.layers)
     high = WanTransformer3DModel(cfg).init_random_weights(dev, seed=1234)
@@ -352,7 +354,8 @@ def run_b200_arm(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD if full_model else f"REDUCED ({args.layers} layers, debug only) " + WORKLOAD,
                    "layers": args.layers, "experts_resident": 2, "guidance_scale": [4.0, 3.0], "flow_shift": 3.0,
-                   "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}", "l2": "inputs larger than L2 (0.77 GB activations)",
+                   "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}" + (" (peer-memory fused exchange)" if (
+                       par.use_p2p and par.sp_size > 1) else (" (NCCL all-to-all)" if par.sp_size > 1 else "")), "l2": "inputs larger than L2 (0.77 GB activations)",
                    "timesteps_run": f"first {args.warmup + args.steps + e2e_steps} of 50"},
         "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel (self-attention, S=75600)", "achieved": achieved,
                      "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,

@@ -175,7 +175,9 @@ def _ulp_report(out, ref):
     frac = mism.float().mean().item()
     # |diff| in units of the bf16 spacing at the reference value; values below 0.25 come out of cancelling O(1)
     # operands (n + n*scale + shift), so their error is measured on the operands' scale
-    spacing = torch.pow(2.0, torch.floor(torch.log2(ref.float().abs().clamp_min(0.25))) - 7)
+    # (a flipped rounding of the intermediate n*(1+scale), |.| up to the row maximum, survives the add of shift)
+    scale_ref = ref.float().abs().amax(dim=-1, keepdim=True).clamp_min(0.25).expand_as(ref)
+    spacing = torch.pow(2.0, torch.floor(torch.log2(scale_ref)) - 7)
     ulps = ((out.float() - ref.float()).abs() / spacing)[mism]
     return frac, (ulps.max().item() if ulps.numel() else 0.0)
 
