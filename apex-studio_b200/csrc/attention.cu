@@ -100,6 +100,12 @@ B200_DEVICE float2 exp2_poly2(float2 x) {
 
 constexpr int POLY_PAIRS = 4;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
 
+B200_DEVICE float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 template <int VARIANT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -297,12 +303,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
               mx3 = __uint_as_float(s[3]);
+        if constexpr (VARIANT >= 4) {
+          // FMNMX3: one instruction folds two new values into an accumulator -> 62 instead of 124 max ops per row
+#pragma unroll
+          for (int k = 4; k < 124; k += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
+          }
+          mx0 = fmax3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
+          mx1 = fmax3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
+        } else {
 #pragma unroll
         for (int k = 4; k < 128; k += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(s[k]));
           mx1 = fmaxf(mx1, __uint_as_float(s[k + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(s[k + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[k + 3]));
+        }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         const float m_new = fmaxf(m, mx * sl2);
@@ -334,7 +353,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int col = c * 32 + 2 * k;
             const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
             float2 e;
-            if (k < POLY_PAIRS) {
+            constexpr int NPOLY = (VARIANT == 5) ? 2 : ((VARIANT == 6) ? 6 : POLY_PAIRS);
+            if (k < NPOLY) {
               e = exp2_poly2(x);
             } else {
               e.x = fast_exp2(x.x);
@@ -532,20 +552,27 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   static int variant = 0;
   if (variant == 0) {
     const char* ev = getenv("B200_ATTN_VARIANT");
-    variant = (ev && ev[0] >= '1' && ev[0] <= '3') ? (ev[0] - '0') : DEFAULT_VARIANT;
-    cudaError_t e1 = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e3 = cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return B200_ERR_LAUNCH;
+    // 4 = 2 + FMNMX3 row max, 5 = 4 with 12.5 % polynomial exps, 6 = 4 with 37.5 %.
+    variant = (ev && ev[0] >= '1' && ev[0] <= '6') ? (ev[0] - '0') : DEFAULT_VARIANT;
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    if (!ok) return B200_ERR_LAUNCH;
   }
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (variant == 1)
-    attn_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-  else if (variant == 2)
-    attn_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-  else
-    attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  switch (variant) {
+    case 1: attn_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 2: attn_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 3: attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 4: attn_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 5: attn_fwd_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    default: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+  }
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

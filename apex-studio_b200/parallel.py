@@ -170,10 +170,6 @@ class PeerExchange:
         self.tokens_total, self.plane = tokens_total, tokens_total * (heads // P) * head_dim
         self.head_off = par.sp_rank * (heads // P)
         self.row0 = par.sp_rank * self.n_local
-        try:  # needed by older torch releases, a no-op / absent in newer ones
-            symm_mem.enable_symm_mem_for_group(par.sp_group.group_name)
-        except Exception:
-            pass
         self.qkv = symm_mem.empty((3, tokens_total, self.width), dtype=torch.bfloat16, device=device)
         self.o = symm_mem.empty((self.n_local, heads * head_dim), dtype=torch.bfloat16, device=device)
         self.h_qkv = symm_mem.rendezvous(self.qkv, par.sp_group)

@@ -319,3 +319,44 @@ def test_denoise_loop_small_vs_oracle():
         x = o.step(n.float().numpy(), int(t), x)
     assert rel_l2(out, torch.from_numpy(x)) <= 2e-2
     assert torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused exchange
+def test_scatter_kernels_addressing_on_one_gpu(ops):
+    """b200_rmsnorm_rope_scatter / b200_attn_fwd_scatter write into 'peer' buffers; here the peers are plain local
+    buffers, which checks the Ulysses addressing (head group -> peer, token -> peer) without NVLink.  The multi-GPU
+    run of the same kernels over symmetric memory is scripts/gpu_mp_check.py (bit-identical to the unsharded path)."""
+    import ctypes
+
+    from apex_studio_b200.wan.rope import wan_rope_table_bf16
+
+    torch.manual_seed(11)
+    P, heads, hd, n_local = 2, 4, 128, 64
+    S_total, width, dim = P * n_local, (heads // P) * hd, heads * hd
+    rank = 1                                   # pretend to be sp rank 1: my tokens are rows 64..127
+    x = torch.randn(n_local, dim, device=DEV).bfloat16()
+    w = (1 + 0.05 * torch.randn(dim, device=DEV)).bfloat16()
+    rope = wan_rope_table_bf16(hd, (2, 8, 8), DEV)[rank * n_local:(rank + 1) * n_local].contiguous()
+    planes = [torch.zeros(3, S_total, width, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    peers = (ctypes.c_void_p * P)(*[t.data_ptr() for t in planes])
+    plane_elems = S_total * width
+    ops.rmsnorm_rope_scatter(x, w, rope, heads, 1e-6, peers, P, 1 * plane_elems, rank * n_local)       # as "k"
+    ops.rmsnorm_rope_scatter(x, None, None, heads, 1e-6, peers, P, 2 * plane_elems, rank * n_local, norm=False)  # "v"
+    ref = ops.rmsnorm_rope_(x.clone(), w, rope, heads, 1e-6)
+    for d in range(P):
+        got_k = planes[d][1, rank * n_local:(rank + 1) * n_local]
+        assert torch.equal(got_k, ref[:, d * width:(d + 1) * width])
+        assert torch.equal(planes[d][2, rank * n_local:(rank + 1) * n_local], x[:, d * width:(d + 1) * width])
+        assert planes[d][0].abs().max().item() == 0 and planes[d][1, :rank * n_local].abs().max().item() == 0
+
+    # attention: this "rank" owns heads [2, 4) of 4; rows 0..127 go to peer 0, rows 128..255 to peer 1
+    S, hp, H_total = 256, 2, 4
+    q, k, v = (torch.randn(1, hp, S, hd, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    obufs = [torch.zeros(S // P, H_total * hd, device=DEV, dtype=torch.bfloat16) for _ in range(P)]
+    opeers = (ctypes.c_void_p * P)(*[t.data_ptr() for t in obufs])
+    ops.attention_scatter(q, k, v, opeers, P, S // P, 2, H_total * hd)
+    ref_o = ops.attention(q, k, v)                       # [1, hp, S, hd]
+    for d in range(P):
+        rows = ref_o[0, :, d * (S // P):(d + 1) * (S // P)]                      # [hp, S/P, hd]
+        assert torch.equal(obufs[d][:, 2 * hd:], rows.transpose(0, 1).reshape(S // P, hp * hd))
+        assert obufs[d][:, :2 * hd].abs().max().item() == 0
