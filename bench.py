@@ -189,9 +189,12 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (no "NCCL version ..." banner)
         dist.init_process_group("nccl", device_id=dev)
-    # B200_P2P=1: Ulysses exchange fused into the kernels over NVLink peer memory instead of NCCL all-to-all
-    use_p2p = os.environ.get("B200_P2P", "0") == "1"
+    # Ulysses exchange fused into the kernels over NVLink peer memory (default; measured 6.7 % faster than the NCCL
+    # all-to-all at N=4 and bit-identical); B200_P2P=0 selects the NCCL exchange.
+    use_p2p = os.environ.get("B200_P2P", "1") == "1"
     par = ParallelContext.create(use_cfg=True, use_p2p=use_p2p) if world > 1 else ParallelContext.single()
 
     cfg = WanConfig(num_layers=args.layers)
