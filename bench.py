@@ -230,6 +230,20 @@ def run_b200_arm(args):
     timed_attention.on = False
     ops.attention = timed_attention
 
+    orig_scatter = ops.attention_scatter   # sequence-parallel form of the same kernel (fused heads->tokens exchange)
+
+    def timed_scatter(q, k, v, *a, **kw):
+        if q.shape[2] == k.shape[2] and q.shape[2] >= 4096 and timed_attention.on:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig_scatter(q, k, v, *a, **kw)
+            e.record()
+            attn_events.append((s, e, q.shape[1], q.shape[2]))
+            return None
+        return orig_scatter(q, k, v, *a, **kw)
+
+    ops.attention_scatter = timed_scatter
+
     state = {"latents": lat_host.to(dev), "pos": pos_host.to(dev), "neg": neg_host.to(dev), "i": 0,
              "host_in": lat_host, "host_out": out_host}
 
