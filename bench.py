@@ -166,7 +166,7 @@ def run_reference_arm(args):
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -396,12 +396,26 @@ def run_b200_arm(args):
             line["cpu_baseline"] = cpu_reference_sample(n_tok=2048, repeats=2)
         except Exception as e:  # keep the GPU line even if the host is too small for the sample
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """Write the ONE result line to the process's real stdout (see main(): fd 1 is pointed at stderr while the
+    benchmark runs so that banners printed by native libraries, e.g. "NCCL version ...", cannot pollute it)."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
