@@ -827,8 +827,33 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   if (H > 65535 || B > 65535) return B200_ERR_SHAPE;
   if ((o_sb % 8) || (o_sh % 8) || (o_ss % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return B200_ERR_ALIGN;
 
+  // B200_ATTN_VARIANT selects the kernel variant for A/B measurements (default DEFAULT_VARIANT):
+  //   1 two-pass bring-up softmax | 2 single pass + f32x2 + 25 % polynomial exp2 | 3 = 2 + split P hand-off
+  //   4 = 2 + FMNMX3 row max | 5 = 4 with 12.5 % polynomial | 6 = 4 with 37.5 %
+  //   7 / 8 / 9 double-buffered S, 64-key steps, with 25 % / 12.5 % / 37.5 % polynomial exps
+  static int variant = 0;
+  if (variant == 0) {
+    const char* ev = getenv("B200_ATTN_VARIANT");
+    variant = (ev && ev[0] >= '1' && ev[0] <= '9') ? (ev[0] - '0') : DEFAULT_VARIANT;
+    bool ok = true;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
+    if (!ok) {
+      variant = 0;
+      return B200_ERR_LAUNCH;
+    }
+  }
+
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[4] = {64, 128, 1, 1};
+  const uint32_t box_kv[4] = {64, variant >= 7 ? 64u : 128u, 1, 1};
   {
     uint64_t dims[4] = {128, (uint64_t)Sq, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)q_ss, (uint64_t)q_sh, (uint64_t)q_sb};
@@ -838,13 +863,13 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   {
     uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)k_ss, (uint64_t)k_sh, (uint64_t)k_sb};
-    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box);
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box_kv);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)v_ss, (uint64_t)v_sh, (uint64_t)v_sb};
-    int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box);
+    int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box_kv);
     if (rc) return rc;
   }
   Params p;
@@ -857,22 +882,6 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.head_off = head_off;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
 
-  // B200_ATTN_VARIANT selects the softmax variant for A/B measurements: 1 = two-pass bring-up version,
-  // 2 = single pass + f32x2 + polynomial exp2 offload, 3 = 2 with the split P hand-off.  Default: DEFAULT_VARIANT.
-  static int variant = 0;
-  if (variant == 0) {
-    const char* ev = getenv("B200_ATTN_VARIANT");
-    // 4 = 2 + FMNMX3 row max, 5 = 4 with 12.5 % polynomial exps, 6 = 4 with 37.5 %.
-    variant = (ev && ev[0] >= '1' && ev[0] <= '6') ? (ev[0] - '0') : DEFAULT_VARIANT;
-    bool ok = true;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    if (!ok) return B200_ERR_LAUNCH;
-  }
   dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (variant) {
@@ -881,7 +890,10 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     case 3: attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 4: attn_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 5: attn_fwd_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    default: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 6: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 7: attn_fwd_db_kernel<4><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    case 8: attn_fwd_db_kernel<2><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    default: attn_fwd_db_kernel<6><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
   }
   B200_CHECK_LAUNCH();
   return B200_OK;
