@@ -477,316 +477,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// =========================================================================================================
-// Double-buffered variant (B200_ATTN_VARIANT 7..9): 64-key steps, TWO S buffers per query tile.
-//
-// In the kernel above S_t(j+1) can only be issued after P_t(j) has been consumed (P aliases S), so each tile's
-// chain is  S -> softmax -> PV -> S -> ...  and the tensor pipe idles whenever both tiles sit in their softmax.
-// Here a step covers 64 keys, so S is 128x64 fp32 = 64 TMEM columns and every tile gets two of them:
-//     TMEM: S(0,0) S(0,1) S(1,0) S(1,1) | O0 | O1        (4 x 64 + 2 x 128 = 512 columns)
-// The MMA warp runs two steps ahead -- S_t(j+2) is issued right after PV_t(j) into the buffer P_t(j) just left --
-// so when a softmax warpgroup finishes step j the scores of step j+1 are already waiting: the softmax side becomes
-// throughput bound (SFU) and its fixed latencies (TMEM load, barrier round trips) are hidden, the tensor pipe
-// always has two independent query tiles to work on.  K/V tiles are 16 KB (64 keys), 8 ring slots, loaded in
-// consumption order K0 K1 V0 K2 V1 K3 ...  O is rescaled lazily by the softmax threads, which now must wait for
-// PV_t(j-1) explicitly (o_done) before touching O_t -- only on the rare steps where the running max jumps.
-// =========================================================================================================
-namespace db {
-constexpr int BKV2 = 64;
-constexpr int KV_TILE = BKV2 * 128 * 2;  // 16 KB: two [64 keys x 64 dims] swizzled halves
-constexpr int KV_HALF = KV_TILE / 2;
-constexpr int SLOTS = 8;
-constexpr int SMEM = 2 * TILE_BYTES + SLOTS * KV_TILE + 1024 + 512;
-}  // namespace db
-
-template <int NPOLY>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-attn_fwd_db_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, Params p) {
-  using namespace db;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_smem = smem;
-  uint8_t* kv_smem = smem + 2 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + SLOTS * KV_TILE);
-  uint64_t* q_full = bars;                  // [1]
-  uint64_t* kv_full = bars + 1;             // [SLOTS]
-  uint64_t* kv_empty = kv_full + SLOTS;     // [SLOTS]
-  uint64_t* s_full = kv_empty + SLOTS;      // [2 tiles][2 buffers]
-  uint64_t* p_full = s_full + 4;            // [2][2]
-  uint64_t* o_done = p_full + 4;            // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_block = blockIdx.x;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int n_kv = (p.Sk + BKV2 - 1) / BKV2;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < SLOTS; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-    }
-    mbar_init(&o_done[0], 1);
-    mbar_init(&o_done[1], 1);
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp >= 8) {
-    setmaxnreg_dec<REGS_OTHER>();
-    if (warp == 8) {
-      // ---------------------------------------------------------------- TMA producer
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-        for (int t = 0; t < 2; ++t) {
-          const int row0 = q_block * (2 * BQ) + t * BQ;
-          tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
-          tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
-        }
-        int slot = 0;
-        uint32_t phase = 0;
-        auto load = [&](const CUtensorMap* tm, int j) {
-          mbar_wait(&kv_empty[slot], phase ^ 1);
-          uint8_t* dst = kv_smem + slot * KV_TILE;
-          mbar_arrive_expect_tx(&kv_full[slot], KV_TILE);
-          tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV2, head, batch);
-          tma_load_4d(dst + KV_HALF, tm, &kv_full[slot], 64, j * BKV2, head, batch);
-          if (++slot == SLOTS) {
-            slot = 0;
-            phase ^= 1;
-          }
-        };
-        load(&tmK, 0);
-        if (n_kv > 1) load(&tmK, 1);
-        for (int j = 0; j < n_kv; ++j) {
-          load(&tmV, j);
-          if (j + 2 < n_kv) load(&tmK, j + 2);
-        }
-      }
-    } else if (warp == 9) {
-      // ---------------------------------------------------------------- MMA issuer
-      if (elect_one()) {
-        constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ, BKV2, 0);
-        constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ, D, 1);
-        const uint32_t q_addr = smem_u32(q_smem);
-        const uint32_t kv_addr = smem_u32(kv_smem);
-        auto s_col = [&](int t, int b) { return tmem_base + static_cast<uint32_t>((t * 2 + b) * BKV2); };
-        auto issue_s = [&](int t, int b, int slot) {
-          const uint32_t a0 = q_addr + t * TILE_BYTES;
-          const uint32_t b0 = kv_addr + slot * KV_TILE;
-#pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk) {
-            umma_ss(s_col(t, b), make_smem_desc_sw128(a0 + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(b0 + (kk >> 2) * KV_HALF + (kk & 3) * 32, 16, 1024), idesc_s,
-                    kk != 0 ? 1u : 0u);
-          }
-        };
-        auto issue_pv = [&](int t, int b, int slot, bool first) {
-          const uint32_t b0 = kv_addr + slot * KV_TILE;
-#pragma unroll
-          for (int kk = 0; kk < BKV2 / 16; ++kk) {
-            umma_ts(tmem_base + 256 + t * 128, s_col(t, b) + kk * 8,
-                    make_smem_desc_sw128(b0 + kk * 2048, KV_HALF, 1024), idesc_o, (first && kk == 0) ? 0u : 1u);
-          }
-        };
-        int slot = 0;
-        uint32_t phase = 0;
-        int cur_slot;
-        uint32_t cur_phase;
-        auto take = [&]() {
-          cur_slot = slot;
-          cur_phase = phase;
-          if (++slot == SLOTS) {
-            slot = 0;
-            phase ^= 1;
-          }
-        };
-        mbar_wait(q_full, 0);
-        for (int j0 = 0; j0 < 2 && j0 < n_kv; ++j0) {  // prologue: S(0), S(1) of both tiles
-          take();
-          mbar_wait(&kv_full[cur_slot], cur_phase);
-          tc_fence_after();
-          issue_s(0, j0, cur_slot);
-          umma_commit(&s_full[0 * 2 + j0]);
-          issue_s(1, j0, cur_slot);
-          umma_commit(&s_full[1 * 2 + j0]);
-          umma_commit(&kv_empty[cur_slot]);
-        }
-        for (int j = 0; j < n_kv; ++j) {
-          const int b = j & 1;
-          const uint32_t par = (j >> 1) & 1;
-          take();
-          const int v_slot = cur_slot;
-          const uint32_t v_phase = cur_phase;
-          const bool has2 = (j + 2 < n_kv);
-          int k_slot = 0;
-          uint32_t k_phase = 0;
-          if (has2) {
-            take();
-            k_slot = cur_slot;
-            k_phase = cur_phase;
-          }
-          mbar_wait(&kv_full[v_slot], v_phase);
-          mbar_wait(&p_full[0 * 2 + b], par);
-          tc_fence_after();
-          issue_pv(0, b, v_slot, j == 0);
-          umma_commit(&o_done[0]);
-          if (has2) {
-            mbar_wait(&kv_full[k_slot], k_phase);
-            tc_fence_after();
-            issue_s(0, b, k_slot);
-            umma_commit(&s_full[0 * 2 + b]);
-          }
-          mbar_wait(&p_full[1 * 2 + b], par);
-          tc_fence_after();
-          issue_pv(1, b, v_slot, j == 0);
-          umma_commit(&o_done[1]);
-          umma_commit(&kv_empty[v_slot]);
-          if (has2) {
-            issue_s(1, b, k_slot);
-            umma_commit(&s_full[1 * 2 + b]);
-            umma_commit(&kv_empty[k_slot]);
-          }
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    setmaxnreg_inc<REGS_SOFTMAX>();
-    const int t = warp >> 2;
-    const int quad = warp & 3;
-    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
-    const float sl2 = p.scale_log2;
-    const float2 sl2_2 = make_float2(sl2, sl2);
-    float m = -INFINITY;
-    float l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1;
-      const uint32_t s_addr = tmem_base + lane_base + static_cast<uint32_t>((t * 2 + b) * BKV2);
-      mbar_wait(&s_full[t * 2 + b], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t s[64];
-      tmem_ld_x32(s_addr + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      tmem_ld_wait();
-      const int valid = p.Sk - j * BKV2;
-      if (valid < BKV2) {
-#pragma unroll
-        for (int k = 0; k < 64; ++k)
-          if (k >= valid) s[k] = 0xff800000u;  // -inf
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-            mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int k = 4; k < 60; k += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-        mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
-        mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
-      }
-      mx0 = fmax3(mx0, __uint_as_float(s[60]), __uint_as_float(s[61]));
-      mx1 = fmax3(mx1, __uint_as_float(s[62]), __uint_as_float(s[63]));
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_new = fmaxf(m, mx * sl2);
-      if (j == 0) {
-        m = m_new;
-      } else if (__any_sync(0xffffffffu, (m_new - m) > RESCALE_THRESHOLD)) {
-        // O_t may still be accumulating P V of step j-1: wait for it before the in-place rescale
-        mbar_wait(&o_done[t], (j - 1) & 1);
-        tc_fence_after();
-        const float alpha = fast_exp2(m - m_new);
-        l *= alpha;
-        m = m_new;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(o_addr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-          tmem_st_x32(o_addr + c * 32, r);
-        }
-        tmem_st_wait();
-      }
-      const float2 negm_2 = make_float2(-m, -m);
-      float2 sum2 = make_float2(0.f, 0.f);
-      uint32_t pk[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float2 x = ffma2(make_float2(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1])), sl2_2, negm_2);
-        float2 e;
-        if ((k & 15) < NPOLY) {
-          e = exp2_poly2(x);
-        } else {
-          e.x = fast_exp2(x.x);
-          e.y = fast_exp2(x.y);
-        }
-        sum2 = fadd2(sum2, e);
-        pk[k] = pack_bf16x2(e.x, e.y);
-      }
-      tmem_st_x32(s_addr, pk);  // P (bf16 pairs) over the first 32 columns of this S buffer
-      l += sum2.x + sum2.y;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t * 2 + b]);
-    }
-    mbar_wait(&o_done[t], (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int row = q_block * (2 * BQ) + t * BQ + quad * 32 + lane;
-    __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
-    if (p.n_peers > 0 && row < p.Sq) {
-      const int d = row / p.rows_per_rank;
-      orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
-             static_cast<int64_t>(head + p.head_off) * p.o_sh;
-    }
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(o_addr + c * 32, r);
-      tmem_ld_wait();
-      if (row < p.Sq) {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 }  // namespace attn
 }  // namespace b200
 
@@ -830,11 +520,13 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   // B200_ATTN_VARIANT selects the kernel variant for A/B measurements (default DEFAULT_VARIANT):
   //   1 two-pass bring-up softmax | 2 single pass + f32x2 + 25 % polynomial exp2 | 3 = 2 + split P hand-off
   //   4 = 2 + FMNMX3 row max | 5 = 4 with 12.5 % polynomial | 6 = 4 with 37.5 %
-  //   7 / 8 / 9 double-buffered S, 64-key steps, with 25 % / 12.5 % / 37.5 % polynomial exps
+  // Measured on B200 (profiles/r01_gpu_session7_attn_ab.log): at 40 heads x 75600^2 every variant >= 2 lands within
+  // 1 % (1213-1228 TFLOP/s) because the run is power-capped (~1.5 GHz); a double-buffered-S design with 64-key steps
+  // was also tried and was no faster, so it was dropped.
   static int variant = 0;
   if (variant == 0) {
     const char* ev = getenv("B200_ATTN_VARIANT");
-    variant = (ev && ev[0] >= '1' && ev[0] <= '9') ? (ev[0] - '0') : DEFAULT_VARIANT;
+    variant = (ev && ev[0] >= '1' && ev[0] <= '6') ? (ev[0] - '0') : DEFAULT_VARIANT;
     bool ok = true;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
@@ -842,9 +534,6 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_db_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, db::SMEM) == cudaSuccess;
     if (!ok) {
       variant = 0;
       return B200_ERR_LAUNCH;
@@ -853,7 +542,6 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
 
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[4] = {64, 128, 1, 1};
-  const uint32_t box_kv[4] = {64, variant >= 7 ? 64u : 128u, 1, 1};
   {
     uint64_t dims[4] = {128, (uint64_t)Sq, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)q_ss, (uint64_t)q_sh, (uint64_t)q_sb};
@@ -863,13 +551,13 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   {
     uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)k_ss, (uint64_t)k_sh, (uint64_t)k_sb};
-    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box_kv);
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box);
     if (rc) return rc;
   }
   {
     uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)v_ss, (uint64_t)v_sh, (uint64_t)v_sb};
-    int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box_kv);
+    int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box);
     if (rc) return rc;
   }
   Params p;
@@ -890,10 +578,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     case 3: attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 4: attn_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 5: attn_fwd_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 6: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 7: attn_fwd_db_kernel<4><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    case 8: attn_fwd_db_kernel<2><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    default: attn_fwd_db_kernel<6><<<grid, NUM_THREADS, db::SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    default: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
   }
   B200_CHECK_LAUNCH();
   return B200_OK;

@@ -148,6 +148,27 @@ blend_tile_kernel(__nv_bfloat16* __restrict__ tile, const __nv_bfloat16* __restr
   }
 }
 
+// Frame hand-off: planar bf16 video [3, T, H, W] in [-1, 1] -> uint8 [T, H, W, 3], with the arithmetic of diffusers'
+// VideoProcessor.postprocess_video: (x * 0.5 + 0.5) in bf16, clamp(0, 1), float * 255, round-half-even, uint8.
+__global__ void __launch_bounds__(256)
+frames_to_uint8_kernel(const __nv_bfloat16* __restrict__ in, uint8_t* __restrict__ out, int T, int64_t hw) {
+  const int64_t total = static_cast<int64_t>(T) * hw;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint8_t px[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __bfloat162float(in[c * total + i]);
+      float y = __bfloat162float(__float2bfloat16(__bfloat162float(__float2bfloat16(x * 0.5f)) + 0.5f));
+      y = fminf(fmaxf(y, 0.0f), 1.0f);
+      px[c] = static_cast<uint8_t>(rintf(y * 255.0f));
+    }
+    out[i * 3 + 0] = px[0];
+    out[i * 3 + 1] = px[1];
+    out[i * 3 + 2] = px[2];
+  }
+}
+
 inline int grid_for(int64_t total, int block) {
   int64_t b = (total + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 32;
@@ -205,6 +226,16 @@ extern "C" int b200_softmax_rows(const float* s, void* p, int rows, int cols, in
   const int64_t threads = static_cast<int64_t>(rows) * 32;
   softmax_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       s, (__nv_bfloat16*)p, rows, cols, lds, ldp, scale);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_frames_to_uint8(const void* video, void* out, int T, int H, int W, void* stream) {
+  if (!video || !out) return B200_ERR_ARG;
+  if (T <= 0 || H <= 0 || W <= 0) return B200_ERR_SHAPE;
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  frames_to_uint8_kernel<<<grid_for(static_cast<int64_t>(T) * hw, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)video, (uint8_t*)out, T, hw);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -131,6 +131,26 @@ def blend_tile(tile: torch.Tensor, up: Optional[torch.Tensor], left: Optional[to
     ops._count()
 
 
+def frames_to_uint8(video: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Frame hand-off after decode: video [3, T, H, W] bf16 in [-1, 1] -> uint8 [T, H, W, 3] on the device, ready for a
+    single D2H copy into the encoder.  Same arithmetic as ``BaseEngine._tensor_to_frames``
+    (engine/base_engine.py:2945-2949 -> diffusers ``VideoProcessor.postprocess_video``: bf16 ``x*0.5+0.5``, clamp,
+    float ``*255``, round-half-even) -- bit-exact, but without the reference's permute / float / PIL passes on the host."""
+    ops._require_cuda_bf16("video", video)
+    if video.dim() != 4 or video.shape[0] != 3 or not video.is_contiguous():
+        raise ValueError(f"video must be contiguous planar [3, T, H, W], got {tuple(video.shape)}")
+    _, T, H, W = video.shape
+    if out is None:
+        out = torch.empty(T, H, W, 3, dtype=torch.uint8, device=video.device)
+    elif out.dtype != torch.uint8 or tuple(out.shape) != (T, H, W, 3) or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 [T, H, W, 3] tensor")
+    lib = _lib.load()
+    rc = lib.b200_frames_to_uint8(video.data_ptr(), out.data_ptr(), T, H, W, _stream())
+    _lib.check(rc, "b200_frames_to_uint8")
+    ops._count()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the decoder
 # ---------------------------------------------------------------------------------------------------------

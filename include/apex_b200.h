@@ -177,6 +177,12 @@ int b200_blend_tile(void* tile, const void* up, const void* left, void* frame, i
                     int up_w, int left_h, int left_w, int blend, int crop_h, int crop_w, int y0, int x0, int OH, int OW,
                     void* stream);
 
+/* Frame hand-off after decode: planar bf16 video [3, T, H, W] in [-1, 1] -> uint8 [T, H, W, 3] (the layout the
+ * encoder / PIL consumes), with the arithmetic of BaseEngine._tensor_to_frames (engine/base_engine.py:2945-2949) ->
+ * diffusers VideoProcessor.postprocess_video on a bf16 tensor: (x * 0.5 + 0.5) in bf16 (two roundings), clamp(0, 1),
+ * float32 * 255, round-half-even, uint8.  Bit-exact. */
+int b200_frames_to_uint8(const void* video, void* out, int T, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,6 +173,19 @@ def vae_decode(latents: torch.Tensor, w: Weights, dtype=torch.float32, **kw) -> 
     return decode(denormalize_latents(latents).to(dtype), w, use_tiling=True, **kw)
 
 
+def frames_to_uint8(video: torch.Tensor):
+    """BaseEngine._tensor_to_frames (engine/base_engine.py:2945-2949) -> diffusers VideoProcessor.postprocess_video
+    (un-vendored dependency, restated from the published code: ``denormalize`` = ``(x * 0.5 + 0.5).clamp(0, 1)`` in the
+    tensor's dtype, ``pt_to_numpy`` = ``.cpu().permute(0, 2, 3, 1).float().numpy()``, ``numpy_to_pil`` =
+    ``(x * 255).round().astype("uint8")``), up to the uint8 arrays PIL wraps.  PARITY UNPINNED for this function: the
+    reference holds no test or golden vector for it.
+    video [3, T, H, W] (the dtype the VAE returned, bf16 on CUDA) -> numpy uint8 [T, H, W, 3]."""
+    x = video.permute(1, 0, 2, 3)                       # postprocess_video: batch_vid = video[b].permute(1, 0, 2, 3)
+    x = (x * 0.5 + 0.5).clamp(0, 1)                     # VaeImageProcessor.denormalize (dtype of the tensor)
+    x = x.cpu().permute(0, 2, 3, 1).float().numpy()     # pt_to_numpy
+    return (x * 255).round().astype("uint8")            # numpy_to_pil
+
+
 def make_weights(*, base_dim: int = 96, z_dim: int = 16, dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2,
                  temporal_upsample=(True, True, False), seed: int = 7, dtype=torch.float32) -> Weights:
     """Synthetic decoder weights with the reference's state-dict keys: conv weights ~ N(0, 1/fan_in) so activations

@@ -174,3 +174,33 @@ def test_vae_decode_vs_reference_golden(name, tiling, sub):
     ref_err, our_err = rel_l2(ref16, exact), rel_l2(got, exact)
     assert our_err <= max(1e-2, 1.5 * ref_err), (our_err, ref_err)
     assert rel_l2(got, ref16) <= 3e-2
+
+
+@pytest.mark.parametrize("T,H,W", [(1, 1, 1), (3, 17, 29), (5, 64, 96)])
+def test_frames_to_uint8_bit_exact(T, H, W):
+    """b200_frames_to_uint8 vs the restated VideoProcessor.postprocess_video arithmetic: integer output, must be ==.
+    Inputs cover the clamp on both sides, exact .5 ties of the final rounding and every bf16 value in [-1.5, 1.5]."""
+    from apex_studio_b200.vae.wan import frames_to_uint8
+
+    g = torch.Generator().manual_seed(T + H + W)
+    v = (torch.randn(3, T, H, W, generator=g) * 0.8).bfloat16()
+    flat = v.view(-1)
+    special = torch.tensor([-1.0, 1.0, -1.5, 1.5, 0.0, -0.0, 1.0 / 255, 0.00390625, 0.99609375], dtype=torch.bfloat16)
+    n = min(flat.numel(), special.numel())
+    flat[:n] = special[:n]
+    got = frames_to_uint8(v.to(DEV))
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (T, H, W, 3)
+    assert np.array_equal(got.cpu().numpy(), wan_vae.frames_to_uint8(v))
+
+
+def test_frames_to_uint8_all_bf16_values():
+    from apex_studio_b200.vae.wan import frames_to_uint8
+
+    bits = torch.arange(0, 65536, dtype=torch.int32).to(torch.int16)
+    allv = bits.view(torch.bfloat16)
+    allv = allv[torch.isfinite(allv.float())]
+    pad = (-allv.numel()) % 3
+    allv = torch.cat([allv, allv[:pad]])
+    v = allv.view(3, 1, 1, -1).contiguous()
+    got = frames_to_uint8(v.to(DEV))
+    assert np.array_equal(got.cpu().numpy(), wan_vae.frames_to_uint8(v))

@@ -55,3 +55,21 @@ def test_channel_padding_and_config_surface():
         AutoencoderKLWan(WanVAEConfig(is_residual=True))
     with pytest.raises(RuntimeError, match="weights not loaded"):
         AutoencoderKLWan().decode(torch.zeros(1, 16, 1, 4, 4))
+
+
+def test_frames_to_uint8_oracle_layout_and_rounding():
+    """The oracle's restatement of VideoProcessor.postprocess_video: layout [T,H,W,3], bf16 x*0.5+0.5, clamp,
+    round-half-even.  (Parity unpinned in the reference; pinned here to hand-computed values.)"""
+    v = torch.tensor([-1.0, 1.0, 0.0, -2.0, 3.0, 1.0 / 255 * 2 - 1], dtype=torch.bfloat16).view(3, 1, 1, 2)
+    out = wan_vae.frames_to_uint8(v)
+    assert out.shape == (1, 1, 2, 3) and out.dtype.name == "uint8"
+    # channel-major input: c0 = (-1, 1), c1 = (0, -2), c2 = (3, ~-0.992)
+    assert out[0, 0, 0].tolist() == [0, 128, 255]            # 0.5 * 255 = 127.5 -> half-even -> 128
+    assert out[0, 0, 1].tolist() == [255, 0, 1]
+
+
+def test_frames_to_uint8_rejects_cpu_tensor():
+    from apex_studio_b200.vae.wan import frames_to_uint8
+
+    with pytest.raises(ValueError):
+        frames_to_uint8(torch.zeros(3, 1, 2, 2, dtype=torch.bfloat16))
