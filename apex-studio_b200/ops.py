@@ -261,3 +261,52 @@ def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance_scale: float)
     _lib.check(rc, "b200_cfg_combine")
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# composite call sites (SURVEY.md section 8b granularity): one C call enqueues the kernels of one reference call site
+# ---------------------------------------------------------------------------------------------------
+def qkv_rmsnorm_rope(x: torch.Tensor, w_qkv: torch.Tensor, b_qkv: Optional[torch.Tensor], wq_norm: torch.Tensor,
+                     wk_norm: torch.Tensor, rope: Optional[torch.Tensor], heads: int, eps: float,
+                     out: torch.Tensor) -> torch.Tensor:
+    """attention.py:345-370 in one call: out[rows, 3*dim] = x @ W_qkv^T + b, then RMS-norm-across-heads + RoPE in place
+    on the q and k column blocks.  Identical launches (and bits) to linear + 2 x rmsnorm_rope_."""
+    for name, t in (("x", x), ("w_qkv", w_qkv), ("wq_norm", wq_norm), ("wk_norm", wk_norm), ("out", out)):
+        _require_cuda_bf16(name, t)
+    rows, dim = x.shape
+    if x.stride(1) != 1 or tuple(w_qkv.shape) != (3 * dim, dim) or not w_qkv.is_contiguous():
+        raise ValueError("x must be [rows, dim] (contiguous rows), w_qkv a contiguous [3*dim, dim]")
+    if tuple(out.shape) != (rows, 3 * dim) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous [{rows}, {3 * dim}] buffer")
+    if rope is not None and (tuple(rope.shape) != (rows, dim // heads) or not rope.is_contiguous()):
+        raise ValueError(f"rope must be contiguous [{rows}, {dim // heads}]")
+    lib = _lib.load()
+    rc = lib.b200_qkv_rmsnorm_rope(x.data_ptr(), w_qkv.data_ptr(), _ptr(b_qkv), wq_norm.data_ptr(), wk_norm.data_ptr(),
+                                   _ptr(rope), out.data_ptr(), rows, dim, heads, x.stride(0), float(eps), _stream())
+    _lib.check(rc, "b200_qkv_rmsnorm_rope")
+    _count(3)
+    return out
+
+
+def mlp_gelu_(h: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+              b2: Optional[torch.Tensor], gate: Optional[torch.Tensor], workspace: torch.Tensor) -> torch.Tensor:
+    """model.py:1265-1279 in one call, in place on the residual stream: h += gate * (W2 gelu_tanh(W1 x + b1) + b2)."""
+    for name, t in (("h", h), ("x", x), ("w1", w1), ("w2", w2), ("workspace", workspace)):
+        _require_cuda_bf16(name, t)
+    rows, dim = x.shape
+    ffn = w1.shape[0]
+    if not (x.is_contiguous() and h.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()):
+        raise ValueError("mlp_gelu_ needs contiguous tensors")
+    if tuple(h.shape) != (rows, dim) or tuple(w1.shape) != (ffn, dim) or tuple(w2.shape) != (dim, ffn):
+        raise ValueError("shape mismatch between h, x, w1, w2")
+    if workspace.numel() < rows * ffn or not workspace.is_contiguous():
+        raise ValueError(f"workspace must hold [{rows}, {ffn}] bf16")
+    if gate is not None:
+        _require_cuda_bf16("gate", gate)
+        gate = gate.reshape(dim).contiguous()
+    lib = _lib.load()
+    rc = lib.b200_mlp_gelu(x.data_ptr(), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), _ptr(gate), h.data_ptr(),
+                           workspace.data_ptr(), rows, dim, ffn, _stream())
+    _lib.check(rc, "b200_mlp_gelu")
+    _count(2)
+    return h

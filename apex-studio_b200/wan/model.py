@@ -31,6 +31,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import ops
+from ..lora import LoraHostMixin
 from ..parallel import ParallelContext
 from .rope import wan_rope_table_bf16
 
@@ -70,7 +71,7 @@ class _Workspace:
         self.kv_ctx = torch.empty(ctx_tokens, 2 * d, dtype=bf, device=device)
 
 
-class WanTransformer3DModel:
+class WanTransformer3DModel(LoraHostMixin):
     """B200 implementation; see module docstring.  Not an nn.Module: weights are a flat dict of bf16 CUDA
     tensors keyed like the reference's state dict (``blocks.N.attn1.to_q.weight`` ...)."""
 
@@ -183,6 +184,22 @@ class WanTransformer3DModel:
         self.w = w
         return self
 
+    def lora_target(self, module: str):
+        """LoRA target module name (reference state-dict naming, e.g. ``blocks.3.attn1.to_k``) -> (weight key in
+        ``self.w``, first row, rows, bias key): resolves the q|k|v / k|v fusion done by ``load_state_dict``."""
+        d = self.config.inner_dim
+        head, _, leaf = module.rpartition(".")
+        fused = None
+        if head.endswith(".attn1") and leaf in ("to_q", "to_k", "to_v"):
+            fused = (head + ".to_qkv", ("to_q", "to_k", "to_v").index(leaf) * d)
+        elif head.endswith(".attn2") and leaf in ("to_k", "to_v"):
+            fused = (head + ".to_kv", ("to_k", "to_v").index(leaf) * d)
+        if fused is not None and fused[0] + ".weight" in self.w:
+            return fused[0] + ".weight", fused[1], d, fused[0] + ".bias"
+        if module + ".weight" in self.w and self.w[module + ".weight"].dim() == 2 and module != "patch_embedding":
+            return module + ".weight", 0, self.w[module + ".weight"].shape[0], module + ".bias"
+        raise ValueError(f"Target module {module} not found in the model (or not a linear layer the b200 path adapts)")
+
     def parameter_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.w.values())
 
@@ -238,11 +255,16 @@ class WanTransformer3DModel:
 
         # 1. self-attention
         ops.layernorm_modulate(h, scale_msa, shift_msa, eps=eps, out=ws.norm)
-        ops.linear(ws.norm, w[p + ".attn1.to_qkv.weight"], w[p + ".attn1.to_qkv.bias"], out=ws.qkv)
+        fused_exchange = par is not None and par.sp_size > 1 and par.use_p2p
+        if fused_exchange:   # q/k norm + RoPE happen inside the scatter kernels below
+            ops.linear(ws.norm, w[p + ".attn1.to_qkv.weight"], w[p + ".attn1.to_qkv.bias"], out=ws.qkv)
+        else:                # attention.py:345-370 as one C call (projection, then norm + RoPE on q and k in place)
+            ops.qkv_rmsnorm_rope(ws.norm, w[p + ".attn1.to_qkv.weight"], w[p + ".attn1.to_qkv.bias"],
+                                 w[p + ".attn1.norm_q.weight"], w[p + ".attn1.norm_k.weight"], rope, heads, eps, ws.qkv)
         q, k, v = ws.qkv[:, :d], ws.qkv[:, d:2 * d], ws.qkv[:, 2 * d:]
         as4 = lambda t, n: t.view(1, n, -1, hd).transpose(1, 2)  # [1,H,n,hd] strided view
         attn_out = ws.attn
-        if par is not None and par.sp_size > 1 and par.use_p2p:
+        if fused_exchange:
             # Ulysses exchange fused into the kernels over NVLink peer memory (parallel.PeerExchange):
             # norm+RoPE(q,k) and a copy of v store straight into the head-owner's planes, the attention epilogue
             # stores straight into the token-owner's [S/P, dim] buffer; two device-side barriers per layer.
@@ -256,11 +278,6 @@ class WanTransformer3DModel:
                                   as4(ex.qkv[2], ex.tokens_total), ex.o_peers, ex.P, ex.n_local, ex.head_off, d)
             ex.barrier(1)
             attn_out = ex.o
-        else:
-            ops.rmsnorm_rope_(q, w[p + ".attn1.norm_q.weight"], rope, heads, eps)
-            ops.rmsnorm_rope_(k, w[p + ".attn1.norm_k.weight"], rope, heads, eps)
-        if par is not None and par.sp_size > 1 and par.use_p2p:
-            pass
         elif par is None or par.sp_size == 1:
             ops.attention(as4(q, S), as4(k, S), as4(v, S), out=as4(ws.attn, S))
         else:
@@ -294,10 +311,8 @@ class WanTransformer3DModel:
 
         # 3. feed-forward
         ops.layernorm_modulate(h, c_scale, c_shift, eps=eps, out=ws.norm)
-        ops.linear(ws.norm, w[p + ".ffn.net.0.proj.weight"], w[p + ".ffn.net.0.proj.bias"],
-                   epilogue=ops.EPI_GELU_TANH, out=ws.ffn)
-        ops.linear(ws.ffn, w[p + ".ffn.net.2.weight"], w[p + ".ffn.net.2.bias"], epilogue=ops.EPI_GATE_RES, out=h,
-                   gate=c_gate)
+        ops.mlp_gelu_(h, ws.norm, w[p + ".ffn.net.0.proj.weight"], w[p + ".ffn.net.0.proj.bias"],
+                      w[p + ".ffn.net.2.weight"], w[p + ".ffn.net.2.bias"], c_gate, ws.ffn)
 
     # ------------------------------------------------------------------------------------ forward
     @torch.inference_mode()

@@ -359,8 +359,10 @@ def run_b200_arm(args):
     traffic = None
     prof = os.path.join(ROOT, "profiles", "attn_ncu_summary.json")
     if os.path.exists(prof):
-        try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+            d = json.load(open(prof))
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            traffic = sum(float(d[k]["value"]) * mult[d[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         except Exception:
             traffic = None
     full_model = args.layers == LAYERS
@@ -376,7 +378,8 @@ def run_b200_arm(args):
                    "timesteps_run": f"first {args.warmup + args.steps + e2e_steps} of 50"},
         "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel (self-attention, S=75600)", "achieved": achieved,
                      "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
-                     "traffic": traffic, "peak_source": peaks["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
+                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, profiles/attn_ncu_summary.json; "
+                     "algorithmic q+k+v+o = 3.10e9)", "peak_source": peaks["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
                      "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg,
                      "kernel_share_of_step": (sum(attn_ms) / args.steps) / ms_step if attn_ms else None,
                      "algorithmic_flops_per_launch": attn_flops},

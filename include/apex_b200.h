@@ -183,6 +183,30 @@ int b200_blend_tile(void* tile, const void* up, const void* left, void* frame, i
  * float32 * 255, round-half-even, uint8.  Bit-exact. */
 int b200_frames_to_uint8(const void* video, void* out, int T, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Composite entry points at the granularity of the reference's call sites.  Each enqueues the
+ * kernels above back to back on `stream`; tensors are contiguous ([rows, dim] unless a stride is given).
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* adaLN modulate: y = LN_fp32(x) * (1 + scale) + shift with scale/shift [dim] shared by all rows
+ * (_chunked_modulated_norm, transformer/wan/base/model.py:56-116). */
+int b200_ln_modulate(const void* x, const void* scale, const void* shift, void* y, int rows, int dim, float eps,
+                     void* stream);
+
+/* Self-attention front end of WanAttnProcessor2_0.__call__ (transformer/wan/base/attention.py:345-370): the fused
+ * to_q|to_k|to_v projection (w_qkv [3*dim, dim], b_qkv [3*dim]) into qkv [rows, 3*dim], then RMS-norm across heads +
+ * RoPE in place on the q and k column blocks (3 launches).  q, k, v for b200_attn_fwd are the column blocks of `qkv`
+ * (head stride head_dim, token stride 3*dim).  x: [rows, dim] with row stride ldx. */
+int b200_qkv_rmsnorm_rope(const void* x, const void* w_qkv, const void* b_qkv, const void* wq_norm, const void* wk_norm,
+                          const void* rope, void* qkv, int rows, int dim, int heads, int64_t ldx, float eps,
+                          void* stream);
+
+/* Feed-forward + gated residual (transformer/wan/base/model.py:1265-1279, diffusers FeedForward "gelu-approximate"):
+ * h += gate * (W2 gelu_tanh(W1 x + b1) + b2); workspace: [rows, ffn_dim] bf16 (2 launches, the activation and the
+ * gate/residual are GEMM epilogues). */
+int b200_mlp_gelu(const void* x, const void* w1, const void* b1, const void* w2, const void* b2, const void* gate,
+                  void* h, void* workspace, int rows, int dim, int ffn_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

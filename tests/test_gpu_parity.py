@@ -360,3 +360,46 @@ def test_scatter_kernels_addressing_on_one_gpu(ops):
         rows = ref_o[0, :, d * (S // P):(d + 1) * (S // P)]                      # [hp, S/P, hd]
         assert torch.equal(obufs[d][:, 2 * hd:], rows.transpose(0, 1).reshape(S // P, hp * hd))
         assert obufs[d][:, :2 * hd].abs().max().item() == 0
+
+
+# ------------------------------------------------------------------------------------------------ composite C entry points
+def test_composite_call_sites_equal_their_parts(ops):
+    """b200_qkv_rmsnorm_rope / b200_mlp_gelu / b200_ln_modulate (SURVEY 8b granularity) enqueue exactly the kernels of
+    the fine-grained entry points: results must be bit-identical."""
+    g = torch.Generator().manual_seed(5)
+    rows, dim, heads, ffn = 333, 256, 2, 640
+    bf = torch.bfloat16
+    x = torch.randn(rows, dim, generator=g).to(DEV, bf)
+    wqkv = (torch.randn(3 * dim, dim, generator=g) * 0.05).to(DEV, bf)
+    bqkv = (torch.randn(3 * dim, generator=g) * 0.05).to(DEV, bf)
+    wq, wk = (1 + 0.1 * torch.randn(dim, generator=g)).to(DEV, bf), (1 + 0.1 * torch.randn(dim, generator=g)).to(DEV, bf)
+    rope = torch.randn(rows, dim // heads, generator=g).to(DEV, bf)
+    ref = ops.linear(x, wqkv, bqkv)
+    ops.rmsnorm_rope_(ref[:, :dim], wq, rope, heads, 1e-6)
+    ops.rmsnorm_rope_(ref[:, dim:2 * dim], wk, rope, heads, 1e-6)
+    out = torch.empty(rows, 3 * dim, dtype=bf, device=DEV)
+    n0 = ops.launch_count
+    ops.qkv_rmsnorm_rope(x, wqkv, bqkv, wq, wk, rope, heads, 1e-6, out)
+    assert ops.launch_count - n0 == 3
+    assert torch.equal(out, ref)
+
+    w1, b1 = (torch.randn(ffn, dim, generator=g) * 0.05).to(DEV, bf), (torch.randn(ffn, generator=g) * 0.05).to(DEV, bf)
+    w2, b2 = (torch.randn(dim, ffn, generator=g) * 0.05).to(DEV, bf), (torch.randn(dim, generator=g) * 0.05).to(DEV, bf)
+    gate = torch.randn(dim, generator=g).to(DEV, bf)
+    h0 = torch.randn(rows, dim, generator=g).to(DEV, bf)
+    h_ref = h0.clone()
+    mid = ops.linear(x, w1, b1, epilogue=ops.EPI_GELU_TANH)
+    ops.linear(mid, w2, b2, epilogue=ops.EPI_GATE_RES, out=h_ref, gate=gate)
+    h = h0.clone()
+    ops.mlp_gelu_(h, x, w1, b1, w2, b2, gate, torch.empty(rows, ffn, dtype=bf, device=DEV))
+    assert torch.equal(h, h_ref)
+
+    from apex_studio_b200 import _lib
+    lib = _lib.load()
+    scale, shift = torch.randn(dim, generator=g).to(DEV, bf), torch.randn(dim, generator=g).to(DEV, bf)
+    y = torch.empty_like(x)
+    rc = lib.b200_ln_modulate(x.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), rows, dim, 1e-6,
+                              torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert torch.equal(y, ops.layernorm_modulate(x, scale, shift, eps=1e-6))
+    assert lib.b200_ln_modulate(x.data_ptr(), None, None, y.data_ptr(), rows, dim, 1e-6, None) == -6

@@ -1,0 +1,169 @@
+"""LoRA hooks: host-side key handling on CPU, merge numerics on the GPU.
+
+Reference: apps/api/src/lora/manager.py:454-606 (load_into -> load_lora_adapter + set_adapters), :383-396, :812-838;
+lora_converter.py:139-163.  Numerics oracle: oracle/lora.py (PEFT runtime form, parity unpinned -- see its header)."""
+import numpy as np
+import pytest
+import torch
+
+import lora as lora_oracle
+import wan_dit
+from apex_studio_b200 import lora as L
+
+DEV = "cuda"
+CFG = dict(dim=256, heads=2, ffn_dim=512, num_layers=2, text_dim=64, freq_dim=256)
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ host logic (CPU)
+def test_strip_adapter_name_and_prefix_detection():
+    st = {"transformer.blocks.0.attn1.to_q.lora_A.default.weight": torch.zeros(4, 8),
+          "transformer.blocks.0.attn1.to_q.lora_B.default.weight": torch.zeros(8, 4)}
+    out = L.strip_adapter_name_from_keys(st)
+    assert sorted(out) == ["transformer.blocks.0.attn1.to_q.lora_A.weight", "transformer.blocks.0.attn1.to_q.lora_B.weight"]
+    assert L.get_prefix_key(list(out)) == "transformer"
+    assert L.get_prefix_key(["blocks.0.x", "transformer.y"]) is None          # first AND last key must carry it
+    assert L.get_prefix_key(["diffusion_model.a", "diffusion_model.b"]) == "diffusion_model"
+    norm = L.normalize_lora_state_dict(st)
+    assert sorted(norm) == ["blocks.0.attn1.to_q.lora_A.weight", "blocks.0.attn1.to_q.lora_B.weight"]
+
+
+def test_alpha_is_folded_like_the_converter():
+    A, B = torch.ones(4, 8), torch.ones(8, 4)
+    st = {"m.lora_down.weight": A, "m.lora_up.weight": B, "m.alpha": torch.tensor(1.0)}
+    out = L.normalize_lora_state_dict(st, prefix=None)
+    assert sorted(out) == ["m.lora_A.weight", "m.lora_B.weight"]
+    # alpha / rank = 0.25 -> scale_down 0.25 doubles while 2*down < up: (0.25, 1) -> (0.5, 0.5)
+    assert torch.allclose(out["m.lora_A.weight"], A * 0.5) and torch.allclose(out["m.lora_B.weight"], B * 0.5)
+    prod = out["m.lora_B.weight"] @ out["m.lora_A.weight"]
+    assert torch.allclose(prod, (B @ A) * 0.25)
+
+
+def test_split_modules_validates_shapes():
+    with pytest.raises(ValueError):
+        L.split_modules({"m.lora_A.weight": torch.zeros(4, 8)})
+    with pytest.raises(ValueError):
+        L.split_modules({"m.lora_A.weight": torch.zeros(4, 8), "m.lora_B.weight": torch.zeros(8, 3)})
+    with pytest.raises(ValueError):
+        L.normalize_lora_state_dict({"m.lora_magnitude_vector": torch.zeros(3)}, prefix=None)
+
+
+def test_lora_target_resolves_fused_projections():
+    from apex_studio_b200.wan import WanConfig, WanTransformer3DModel
+
+    m = WanTransformer3DModel(WanConfig(num_attention_heads=2, text_dim=64, ffn_dim=512, num_layers=1))
+    m.load_state_dict(wan_dit.make_weights(**dict(CFG, num_layers=1), seed=1, dtype=torch.float32), device="cpu")
+    assert m.lora_target("blocks.0.attn1.to_k") == ("blocks.0.attn1.to_qkv.weight", 256, 256, "blocks.0.attn1.to_qkv.bias")
+    assert m.lora_target("blocks.0.attn2.to_v") == ("blocks.0.attn2.to_kv.weight", 256, 256, "blocks.0.attn2.to_kv.bias")
+    assert m.lora_target("blocks.0.attn2.to_q")[:3] == ("blocks.0.attn2.to_q.weight", 0, 256)
+    assert m.lora_target("blocks.0.ffn.net.0.proj")[:3] == ("blocks.0.ffn.net.0.proj.weight", 0, 512)
+    with pytest.raises(ValueError):
+        m.lora_target("blocks.0.attn1.nope")
+    with pytest.raises(ValueError):
+        m.lora_target("patch_embedding")
+    # the PeftAdapterMixin surface the manager probes (manager.py:470-486)
+    assert hasattr(m, "set_adapters") and hasattr(m, "load_lora_adapter")
+    w = wan_dit.make_weights(**dict(CFG, num_layers=1), seed=1, dtype=torch.float32)
+    lo = lora_oracle.make_lora(w, ["blocks.0.attn1.to_q"], rank=4)
+    m.load_lora_adapter({"transformer." + k: v for k, v in lo.items()}, adapter_name="a", prefix="transformer")
+    assert list(m.peft_config) == ["a"] and m.peft_config["a"]["r"] == 4
+    with pytest.raises(ValueError):
+        m.load_lora_adapter(lo, adapter_name="a", prefix=None)            # duplicate adapter name
+    with pytest.raises(ValueError):
+        m.set_adapters(["missing"], [1.0])
+    with pytest.raises(ValueError):
+        m.set_adapters(["a"], [1.0, 2.0])
+    with pytest.raises(ValueError):                                        # no CPU fallback: the merge is a CUDA GEMM
+        m.set_adapters(["a"], [1.0])
+
+
+def test_oracle_runtime_form_equals_merged_weight():
+    g = torch.Generator().manual_seed(3)
+    x, W, b = torch.randn(5, 16, generator=g), torch.randn(12, 16, generator=g), torch.randn(12, generator=g)
+    ads = [(torch.randn(4, 16, generator=g), torch.randn(12, 4, generator=g), 0.7),
+           (torch.randn(2, 16, generator=g), torch.randn(12, 2, generator=g), -1.3)]
+    y1 = lora_oracle.lora_linear_runtime(x, W, b, ads)
+    y2 = torch.nn.functional.linear(x, lora_oracle.merged_weight(W, ads), b)
+    assert torch.allclose(y1, y2, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _model():
+    from apex_studio_b200.wan import WanConfig, WanTransformer3DModel
+
+    w32 = wan_dit.make_weights(**CFG, seed=1234, dtype=torch.float32)
+    m = WanTransformer3DModel(WanConfig(num_attention_heads=2, text_dim=64, ffn_dim=512, num_layers=2))
+    m.load_state_dict(w32, device=DEV)
+    return m, w32
+
+
+MODULES = ["blocks.0.attn1.to_q", "blocks.0.attn1.to_k", "blocks.0.attn1.to_v", "blocks.0.attn1.to_out.0",
+           "blocks.1.attn2.to_q", "blocks.1.attn2.to_k", "blocks.1.attn2.to_v", "blocks.1.ffn.net.0.proj",
+           "blocks.1.ffn.net.2", "condition_embedder.time_proj"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rank", [4, 16, 36, 128])
+def test_merge_equals_fp32_math_and_unmerge_is_bit_exact(rank):
+    m, w32 = _model()
+    base = {k: v.clone() for k, v in m.w.items()}
+    lo = lora_oracle.make_lora(w32, MODULES, rank=rank, seed=rank)
+    m.load_lora_adapter(lo, adapter_name="x", prefix=None)
+    m.set_adapters(["x"], [0.8])
+    for mod in MODULES:
+        wkey, r0, rows, _ = m.lora_target(mod)
+        got = m.w[wkey][r0:r0 + rows].float().cpu()
+        # same operands the kernel saw: bf16 base, bf16(0.8 * B), bf16 A; fp32 accumulate; one rounding
+        A16, B16 = lo[mod + ".lora_A.weight"].bfloat16().float(), (lo[mod + ".lora_B.weight"] * 0.8).bfloat16().float()
+        want = (base[wkey][r0:r0 + rows].float().cpu() + B16 @ A16)
+        ulp = (want.abs().clamp_min(2.0 ** -126)).log2().floor().exp2() * 2.0 ** -7
+        err = (got - want).abs() / ulp                                  # correctly rounded, up to the fp32 summation order
+        assert err.max() <= 1.0 and (err > 0.51).float().mean() < 1e-3, (mod, err.max().item())
+        # and close to the exact (unrounded factors) merge
+        exact = lora_oracle.merged_weight(w32[mod + ".weight"], [(lo[mod + ".lora_A.weight"], lo[mod + ".lora_B.weight"], 0.8)])
+        assert rel_l2(got, exact) <= 4e-3
+    untouched = [k for k in base if not any(m.lora_target(mod)[0] == k for mod in MODULES)]
+    assert all(torch.equal(m.w[k], base[k]) for k in untouched)
+    m.set_adapters(["x"], [0.0])
+    assert all(torch.equal(m.w[k], base[k]) for k in base)
+    m.set_adapters(["x"], [1.0])
+    m.delete_adapters("x")
+    assert all(torch.equal(m.w[k], base[k]) for k in base) and m.peft_config == {}
+
+
+@pytest.mark.gpu
+def test_two_adapters_forward_vs_oracle_runtime_form():
+    """DiT forward with two active adapters vs the exact-math oracle with the adapters merged in fp32 (== PEFT's
+    runtime form by linearity).  Tolerance: the same bar as the un-adapted forward (rel-L2 <= max(1e-3, 1.5 x the bf16
+    error of the oracle run in bf16))."""
+    import os
+
+    from conftest import GOLDEN
+
+    m, w32 = _model()
+    g = np.load(os.path.join(GOLDEN, "dit_s72.npz"))
+    lat, t, text = torch.from_numpy(g["latents"]), torch.from_numpy(g["timestep"]), torch.from_numpy(g["text"])
+    mods = [f"blocks.{i}.{n}" for i in range(2) for n in ("attn1.to_q", "attn1.to_k", "attn1.to_v", "attn1.to_out.0",
+                                                           "attn2.to_q", "attn2.to_k", "attn2.to_v", "attn2.to_out.0",
+                                                           "ffn.net.0.proj", "ffn.net.2")]
+    lo1 = lora_oracle.make_lora(w32, mods, rank=16, seed=1)
+    lo2 = lora_oracle.make_lora(w32, mods[::2], rank=8, seed=2)
+    m.load_lora_adapter({"transformer." + k: v for k, v in lo1.items()}, adapter_name="lightning", prefix="transformer")
+    m.load_lora_adapter({k.replace(".weight", ".default.weight"): v for k, v in lo2.items()}, adapter_name="style", prefix=None)
+    m.set_adapters(["lightning", "style"], [1.0, 0.6])
+    assert m.active_adapters() == ["lightning", "style"]
+    out = m(lat.to(DEV, torch.bfloat16), t.to(DEV), text.to(DEV, torch.bfloat16), return_dict=False)[0]
+    wm = lora_oracle.merge_into_state_dict(lora_oracle.merge_into_state_dict(w32, lo1, 1.0), lo2, 0.6)
+    kw = dict(heads=2, num_layers=2, freq_dim=256)
+    exact = wan_dit.dit_forward(lat, t, text, wm, **kw)
+    bf = wan_dit.dit_forward(lat.bfloat16(), t, text.bfloat16(), {k: v.bfloat16() for k, v in wm.items()}, **kw)
+    base_out = wan_dit.dit_forward(lat, t, text, w32, **kw)
+    assert rel_l2(exact, base_out) > 5e-2                       # the adapters really change the output
+    assert rel_l2(out, exact) <= max(1e-3, 1.5 * rel_l2(bf, exact)), (rel_l2(out, exact), rel_l2(bf, exact))
+    m.disable_lora()
+    out0 = m(lat.to(DEV, torch.bfloat16), t.to(DEV), text.to(DEV, torch.bfloat16), return_dict=False)[0]
+    assert rel_l2(out0, torch.from_numpy(g["out_bf16"])) <= 2e-2
