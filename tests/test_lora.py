@@ -121,7 +121,11 @@ def test_merge_equals_fp32_math_and_unmerge_is_bit_exact(rank):
         A16, B16 = lo[mod + ".lora_A.weight"].bfloat16().float(), (lo[mod + ".lora_B.weight"] * 0.8).bfloat16().float()
         want = (base[wkey][r0:r0 + rows].float().cpu() + B16 @ A16)
         ulp = (want.abs().clamp_min(2.0 ** -126)).log2().floor().exp2() * 2.0 ** -7
-        err = (got - want).abs() / ulp                                  # correctly rounded, up to the fp32 summation order
+        # correctly rounded, up to the fp32 summation order: where base and delta cancel (|want| << |base|) the
+        # accumulation error (<= (r + 1) * 2^-24 * sum of magnitudes) is not small against ulp(want), so it is allowed for
+        # explicitly (an element with want ~ 3e-8 missed the plain 1-ulp bar by 4 ulp on the GPU, rank 36)
+        acc = (rank + 1) * 2.0 ** -24 * (base[wkey][r0:r0 + rows].float().cpu().abs() + B16.abs() @ A16.abs())
+        err = ((got - want).abs() - acc).clamp_min(0) / ulp
         assert err.max() <= 1.0 and (err > 0.51).float().mean() < 1e-3, (mod, err.max().item())
         # and close to the exact (unrounded factors) merge
         exact = lora_oracle.merged_weight(w32[mod + ".weight"], [(lo[mod + ".lora_A.weight"], lo[mod + ".lora_B.weight"], 0.8)])
