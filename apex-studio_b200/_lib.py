@@ -32,6 +32,9 @@ SIGNATURES = {
     "b200_softmax_rows": (_i, [_p, _p, _i, _i, _i64, _i64, _f, _p]),
     "b200_blend_tile": (_i, [_p, _p, _p, _p] + [_i] * 14 + [_p]),
     "b200_frames_to_uint8": (_i, [_p, _p, _i, _i, _i, _p]),
+    "b200_adaln_zero_modulate": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _f, _p]),
+    "b200_headnorm_rope": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _f, _i, _p]),
+    "b200_swiglu": (_i, [_p, _p, _i, _i, _i64, _i64, _p]),
     "b200_ln_modulate": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "b200_qkv_rmsnorm_rope": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i64, _f, _p]),
     "b200_mlp_gelu": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),

@@ -44,7 +44,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // LayerNorm (fp32 statistics, two-pass) + optional affine + optional (1+scale), shift modulation.
 // reference: FP32LayerNorm -> .to(bf16); x.addcmul_(x, scale); x.add_(shift)   (model.py:56-116, ops.py:37-56)
 // ------------------------------------------------------------------------------------------------
-template <int THREADS>
+// MODE 0: Wan (above).  MODE 1: diffusers AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous and the
+// explicit `norm2(x) * (1 + scale) + shift` of the dual-stream blocks (flux/base/model.py:266,297-300,
+// hunyuanvideo15/base/model.py:617-694): nn.LayerNorm in bf16 (fp32 inside, one rounding), then three bf16 tensor ops
+// s1 = bf16(1 + scale); y = bf16(y * s1); y = bf16(y + shift).
+template <int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS)
 layernorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                           const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift,
@@ -114,7 +118,8 @@ layernorm_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __
         unpack8(__ldg(sh + c), b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float t = round_bf16(f[j] + f[j] * a[j]);  // addcmul_(x, scale)
+          const float t = MODE == 0 ? round_bf16(f[j] + f[j] * a[j])              // addcmul_(x, scale)
+                                    : round_bf16(f[j] * round_bf16(1.0f + a[j])); // norm(x) * (1 + scale)
           f[j] = t + b[j];                                 // add_(shift), rounded by pack8
         }
       }
@@ -276,9 +281,9 @@ using namespace b200::ew;
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int b200_layernorm_modulate(const void* x, void* y, const void* scale, const void* shift, const void* ln_w,
-                                       const void* ln_b, int rows, int dim, int64_t ldx, int64_t ldy,
-                                       int64_t mod_stride, float eps, void* stream) {
+static int layernorm_modulate_launch(const void* x, void* y, const void* scale, const void* shift, const void* ln_w,
+                                     const void* ln_b, int rows, int dim, int64_t ldx, int64_t ldy,
+                                     int64_t mod_stride, float eps, int mode, void* stream) {
   if (!x || !y) return B200_ERR_ARG;
   if ((scale == nullptr) != (shift == nullptr)) return B200_ERR_ARG;
   if (rows <= 0 || dim <= 0) return B200_ERR_SHAPE;
@@ -288,14 +293,30 @@ extern "C" int b200_layernorm_modulate(const void* x, void* y, const void* scale
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = dispatch_threads(dim / 8, [&](auto T) {
     constexpr int THREADS = decltype(T)::value;
-    layernorm_modulate_kernel<THREADS><<<rows, THREADS, 0, st>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift,
-        (const __nv_bfloat16*)ln_w, (const __nv_bfloat16*)ln_b, dim, ldx, ldy, mod_stride, eps);
+    if (mode == 0)
+      layernorm_modulate_kernel<THREADS, 0><<<rows, THREADS, 0, st>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift,
+          (const __nv_bfloat16*)ln_w, (const __nv_bfloat16*)ln_b, dim, ldx, ldy, mod_stride, eps);
+    else
+      layernorm_modulate_kernel<THREADS, 1><<<rows, THREADS, 0, st>>>(
+          (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)scale, (const __nv_bfloat16*)shift,
+          (const __nv_bfloat16*)ln_w, (const __nv_bfloat16*)ln_b, dim, ldx, ldy, mod_stride, eps);
     return B200_OK;
   });
   if (rc) return rc;
   B200_CHECK_LAUNCH();
   return B200_OK;
+}
+
+extern "C" int b200_layernorm_modulate(const void* x, void* y, const void* scale, const void* shift, const void* ln_w,
+                                       const void* ln_b, int rows, int dim, int64_t ldx, int64_t ldy,
+                                       int64_t mod_stride, float eps, void* stream) {
+  return layernorm_modulate_launch(x, y, scale, shift, ln_w, ln_b, rows, dim, ldx, ldy, mod_stride, eps, 0, stream);
+}
+
+extern "C" int b200_adaln_zero_modulate(const void* x, void* y, const void* scale, const void* shift, int rows, int dim,
+                                        int64_t ldx, int64_t ldy, float eps, void* stream) {
+  return layernorm_modulate_launch(x, y, scale, shift, nullptr, nullptr, rows, dim, ldx, ldy, 0, eps, 1, stream);
 }
 
 static int rmsnorm_rope_launch(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,

@@ -100,3 +100,30 @@ def base_denoise(**kwargs) -> torch.Tensor:
     kwargs.pop("low_noise_transformer", None)
     kwargs["boundary_timestep"] = None
     return moe_denoise(high_noise_transformer=transformer, low_noise_transformer=None, **kwargs)
+
+
+@torch.inference_mode()
+def flux_denoise(*, latents: torch.Tensor, timesteps: torch.Tensor, scheduler, transformer, prompt_embeds: torch.Tensor,
+                 pooled_prompt_embeds: torch.Tensor, latent_ids: torch.Tensor, text_ids: torch.Tensor,
+                 guidance: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_pooled_prompt_embeds: Optional[torch.Tensor] = None, negative_text_ids: Optional[torch.Tensor] = None,
+                 true_cfg_scale: float = 1.0, use_cfg_guidance: bool = False,
+                 denoise_progress_callback: Optional[Callable] = None) -> torch.Tensor:
+    """``FluxShared.base_denoise`` (apps/api/src/engine/flux/shared.py:504-620) with the same keyword names: per step one
+    forward on the packed latents [B, S_img, 64] at ``timestep / 1000`` (plus the negative-prompt forward and
+    ``neg + s * (pos - neg)`` when true CFG is on, :561-582), then ``scheduler.step``.  FLUX.1-dev is guidance-distilled:
+    ``guidance`` is embedded (:150-156 of t2i.py) and true CFG is normally off."""
+    total = len(timesteps)
+    for i, t in enumerate(timesteps):
+        timestep = t.expand(latents.shape[0]).to(latents.dtype)
+        kw = dict(hidden_states=latents, timestep=timestep / 1000, guidance=guidance, img_ids=latent_ids, return_dict=False)
+        noise_pred = transformer(pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
+                                 txt_ids=text_ids, **kw)[0]
+        if use_cfg_guidance:
+            neg = transformer(pooled_projections=negative_pooled_prompt_embeds, encoder_hidden_states=negative_prompt_embeds,
+                              txt_ids=negative_text_ids, **kw)[0]
+            noise_pred = ops.cfg_combine(noise_pred, neg, float(true_cfg_scale))
+        latents = scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+        if denoise_progress_callback is not None:
+            denoise_progress_callback(float(i + 1) / float(total), f"Denoise {i + 1}/{total}")
+    return latents

@@ -264,6 +264,83 @@ def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guidance_scale: float)
 
 
 # ---------------------------------------------------------------------------------------------------
+# dual-stream (MMDiT) families: Flux, HunyuanVideo-1.5, QwenImage
+# ---------------------------------------------------------------------------------------------------
+NORM_NONE, NORM_TORCH_RMS, NORM_INPLACE_RMS, NORM_DIFFUSERS_RMS = 0, 1, 2, 3
+
+
+def adaln_zero_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, *, eps: float = 1e-6,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``LayerNorm(x) * (1 + scale) + shift`` with the rounding points of diffusers' AdaLayerNormZero family
+    (flux/base/model.py:266-272,297-300); x [rows, dim] (row stride free), scale/shift [dim]."""
+    _require_cuda_bf16("x", x)
+    _require_cuda_bf16("scale", scale)
+    _require_cuda_bf16("shift", shift)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [rows, dim] with a contiguous last dim")
+    rows, dim = x.shape
+    scale, shift = scale.reshape(-1), shift.reshape(-1)
+    if scale.numel() != dim or shift.numel() != dim or scale.stride(0) != 1 or shift.stride(0) != 1:
+        raise ValueError(f"scale/shift must be contiguous [{dim}] vectors")
+    if out is None:
+        out = torch.empty((rows, dim), dtype=x.dtype, device=x.device)
+    if tuple(out.shape) != (rows, dim) or out.stride(1) != 1:
+        raise ValueError(f"out must be [{rows}, {dim}] with a contiguous last dim")
+    _require_cuda_bf16("out", out)
+    rc = _lib.load().b200_adaln_zero_modulate(x.data_ptr(), out.data_ptr(), scale.data_ptr(), shift.data_ptr(), rows, dim,
+                                              x.stride(0), out.stride(0), float(eps), _stream())
+    _lib.check(rc, "b200_adaln_zero_modulate")
+    _count()
+    return out
+
+
+def headnorm_rope_(q: torch.Tensor, k: Optional[torch.Tensor], wq: Optional[torch.Tensor], wk: Optional[torch.Tensor],
+                   rope: Optional[torch.Tensor], heads: int, eps: float = 1e-6, norm_mode: int = NORM_TORCH_RMS) -> None:
+    """In place on q (and k): per-head RMS-norm over head_dim = 128, then rotation of (even, odd) channel pairs.
+
+    q, k: [rows, heads*128] column blocks of one buffer (same row stride); rope: fp32 [rows, 64, 2] = (cos, sin)."""
+    _require_cuda_bf16("q", q)
+    if q.dim() != 2 or q.stride(1) != 1 or q.shape[1] != heads * 128:
+        raise ValueError(f"q must be [rows, {heads * 128}] with a contiguous last dim (head_dim 128 only)")
+    rows = q.shape[0]
+    if k is not None:
+        _require_cuda_bf16("k", k)
+        if tuple(k.shape) != tuple(q.shape) or k.stride() != q.stride():
+            raise ValueError("k must have q's shape and strides")
+    for name, t in (("wq", wq), ("wk", wk)):
+        if t is not None:
+            _require_cuda_bf16(name, t)
+            if t.numel() != 128 or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous [128] gain")
+    if rope is not None:
+        if not rope.is_cuda or rope.dtype != torch.float32 or tuple(rope.shape) != (rows, 64, 2) or not rope.is_contiguous():
+            raise ValueError(f"rope must be a contiguous CUDA float32 [{rows}, 64, 2] (cos, sin) table")
+    if norm_mode not in (0, 1, 2, 3):
+        raise ValueError(f"norm_mode {norm_mode}")
+    rc = _lib.load().b200_headnorm_rope(q.data_ptr(), _ptr(k), _ptr(wq), _ptr(wk), _ptr(rope), rows, heads, 128,
+                                        q.stride(0), float(eps), norm_mode, _stream())
+    _lib.check(rc, "b200_headnorm_rope")
+    _count()
+
+
+def swiglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """silu(x[:, :inner]) * x[:, inner:] (Flux2SwiGLU, flux2/base/model.py:91-105); x [rows, 2*inner]."""
+    _require_cuda_bf16("x", x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 2:
+        raise ValueError("x must be [rows, 2*inner] with a contiguous last dim")
+    rows, inner = x.shape[0], x.shape[1] // 2
+    if out is None:
+        out = torch.empty((rows, inner), dtype=x.dtype, device=x.device)
+    _require_cuda_bf16("out", out)
+    if tuple(out.shape) != (rows, inner) or out.stride(1) != 1:
+        raise ValueError(f"out must be [{rows}, {inner}] with a contiguous last dim")
+    rc = _lib.load().b200_swiglu(x.data_ptr(), out.data_ptr(), rows, inner, x.stride(0), out.stride(0), _stream())
+    _lib.check(rc, "b200_swiglu")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # composite call sites (SURVEY.md section 8b granularity): one C call enqueues the kernels of one reference call site
 # ---------------------------------------------------------------------------------------------------
 def qkv_rmsnorm_rope(x: torch.Tensor, w_qkv: torch.Tensor, b_qkv: Optional[torch.Tensor], wq_norm: torch.Tensor,

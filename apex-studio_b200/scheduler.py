@@ -249,3 +249,70 @@ def get_timesteps(scheduler: UniPCMultistepScheduler, num_inference_steps: Optio
         ts = ts[t_start * scheduler.order:]
         num_inference_steps = len(ts)
     return ts, num_inference_steps
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """Flow-matching Euler scheduler the Flux manifests name (``diffusers.FlowMatchEulerDiscreteScheduler``,
+    apps/api/manifest/image/flux-dev-text-to-image-1.0.0.v1.yml:38-46) with the FLUX.1-dev scheduler config
+    (``use_dynamic_shifting=True``, exponential time shift).  The class lives in the un-vendored ``diffusers``
+    dependency; this restates its published algorithm for the calls the Flux engine makes
+    (engine/flux/t2i.py:110-135 ``set_timesteps(sigmas=linspace(1, 1/N, N), mu=...)``, engine/flux/shared.py:584-588
+    ``step``) -- parity UNPINNED (no in-tree twin, no reference test).  ``step`` is two fp32 element-wise ops on the
+    device (the latents of a 1024x1024 image are 262k elements)."""
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 3.0, use_dynamic_shifting: bool = True,
+                 base_shift: float = 0.5, max_shift: float = 1.15, base_image_seq_len: int = 256,
+                 max_image_seq_len: int = 4096):
+        self.num_train_timesteps, self.shift, self.use_dynamic_shifting = num_train_timesteps, shift, use_dynamic_shifting
+        self.base_shift, self.max_shift = base_shift, max_shift
+        self.base_image_seq_len, self.max_image_seq_len = base_image_seq_len, max_image_seq_len
+        self.config = self
+        self.timesteps = self.sigmas = None
+        self._step_index = self._begin_index = None
+
+    def get(self, name, default=None):  # the engine reads scheduler.config.get("base_shift", 0.5) (t2i.py:121-127)
+        return getattr(self, name, default)
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    def set_begin_index(self, begin_index: int = 0) -> None:
+        self._begin_index = begin_index
+
+    def set_timesteps(self, num_inference_steps: Optional[int] = None, device=None, sigmas=None, mu: Optional[float] = None):
+        if self.use_dynamic_shifting and mu is None:
+            raise ValueError("`mu` must be passed when `use_dynamic_shifting` is set to be `True`")
+        if sigmas is None:
+            ts = np.linspace(float(self.num_train_timesteps), 1.0, num_inference_steps)  # sigma_max=1, sigma_min=1/1000
+            sigmas = ts / self.num_train_timesteps
+        sigmas = np.array(sigmas).astype(np.float32)
+        if self.use_dynamic_shifting:
+            sigmas = math.exp(mu) / (math.exp(mu) + (1 / sigmas - 1) ** 1.0)
+        else:
+            sigmas = self.shift * sigmas / (1 + (self.shift - 1) * sigmas)
+        sig = torch.from_numpy(np.asarray(sigmas)).to(dtype=torch.float32, device=device)
+        self.timesteps = sig * self.num_train_timesteps
+        self.sigmas = torch.cat([sig, torch.zeros(1, device=sig.device)])
+        self._step_index = None
+        return self.timesteps
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = False, **unused):
+        if self._step_index is None:
+            self._step_index = self._begin_index or 0
+        i = self._step_index
+        # upstream: ``dt = sigma_next - sigma`` (0-dim fp32 tensors); ``sample.float() + dt * model_output`` -- with a
+        # bf16 model_output torch's type promotion makes the product a bf16 op (0-dim operands do not promote)
+        dt = self.sigmas[i + 1] - self.sigmas[i]
+        prev = sample.to(torch.float32) + dt * model_output
+        self._step_index += 1
+        return (prev.to(model_output.dtype),)
+
+
+def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.15) -> float:
+    """FluxShared.calculate_shift (engine/flux/shared.py:58-70): the ``mu`` of the dynamic time shift."""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b

@@ -184,6 +184,33 @@ int b200_blend_tile(void* tile, const void* up, const void* left, void* frame, i
 int b200_frames_to_uint8(const void* video, void* out, int T, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Dual-stream (MMDiT) block families -- Flux, HunyuanVideo-1.5, QwenImage.  They reach the
+ * attention core and the GEMM above unchanged; these are their row kernels.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* diffusers AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous and the explicit
+ * `norm2(x) * (1 + scale) + shift` of the dual-stream blocks: y = bf16(bf16(bf16(LN(x)) * bf16(1 + scale)) + shift),
+ * LN without affine, fp32 statistics; scale/shift [dim] shared by all rows.
+ * Replaces flux/base/model.py:266-272,297-300,320-324,215,649; hunyuanvideo15/base/model.py:634-639,664-673;
+ * qwenimage/base/model.py:679-750 (_modulate). */
+int b200_adaln_zero_modulate(const void* x, void* y, const void* scale, const void* shift, int rows, int dim,
+                             int64_t ldx, int64_t ldy, float eps, void* stream);
+
+/* Per-head q/k RMS-norm (over head_dim = 128) + rotary embedding on interleaved channel pairs, in place on the q and k
+ * column blocks of a fused QKV buffer (row stride ldx), both tensors in one launch (k, wq, wk, rope may be NULL).
+ *   norm_mode 0: no norm; 1: torch.nn.RMSNorm rounding (flux/base/attention.py:70-71,78-79);
+ *             2: InplaceRMSNorm rounding (efficiency/mod.py:24-35 as used hunyuanvideo15/base/model.py:115-116,142-145);
+ *             3: diffusers RMSNorm rounding (qwenimage/base/attention.py:115-122).
+ *   rope: fp32 [rows, 64, 2] = (cos, sin) per channel pair; re' = re*c - im*s, im' = im*c + re*s in fp32, one rounding
+ *         (flux/base/attention.py:86-88; efficiency/ops.py:163-235; qwenimage/base/attention.py:124-130). */
+int b200_headnorm_rope(void* q, void* k, const void* wq, const void* wk, const float* rope, int rows, int heads,
+                       int head_dim, int64_t ldx, float eps, int norm_mode, void* stream);
+
+/* SwiGLU of a fused projection: y[:, j] = bf16(bf16(silu(x[:, j])) * x[:, inner + j]), x [rows, 2*inner] (row stride
+ * ldx), y [rows, inner] (row stride ldy).  Replaces Flux2SwiGLU.forward, flux2/base/model.py:91-105. */
+int b200_swiglu(const void* x, void* y, int rows, int inner, int64_t ldx, int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Composite entry points at the granularity of the reference's call sites.  Each enqueues the
  * kernels above back to back on `stream`; tensors are contiguous ([rows, dim] unless a stride is given).
  * --------------------------------------------------------------------------------------------------------- */

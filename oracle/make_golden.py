@@ -166,9 +166,68 @@ def golden_vae():
     print("vae", {k: v.shape for k, v in out.items()})
 
 
+FLUX_CONFIGS = {
+    # name: (oracle make_weights kwargs, latent grid (h, w), text tokens)
+    "flux_s56": (dict(dim=256, heads=2, num_layers=2, num_single_layers=2, in_channels=16, joint_dim=32, pooled_dim=24,
+                      guidance_embeds=True), (6, 8), 8),
+    "flux_s200": (dict(dim=256, heads=2, num_layers=1, num_single_layers=1, in_channels=16, joint_dim=32, pooled_dim=24,
+                       guidance_embeds=False), (12, 16), 8),
+}
+
+
+def golden_flux():
+    """Reference FluxTransformer2DModel (transformer/flux/base/model.py) with the `sdpa` backend on seeded inputs, fp32
+    and bf16: final output plus pins after the embedders, the first dual-stream and the first single-stream block.
+    timestep 0.5 and guidance 4.0 are exactly representable after the reference's bf16 `* 1000`."""
+    import flux_dit
+
+    fm = bootstrap.ref("src.transformer.flux.base.model")
+    a = bootstrap.ref("src.attention.functions")
+    a.attention_register.set_default("sdpa")
+    for name, (cfg, (gh, gw), n_txt) in FLUX_CONFIGS.items():
+        w32 = flux_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+        x = torch.randn(1, gh * gw, cfg["in_channels"], generator=torch.Generator().manual_seed(42))
+        enc = torch.randn(1, n_txt, cfg["joint_dim"], generator=torch.Generator().manual_seed(43))
+        pooled = torch.randn(1, cfg["pooled_dim"], generator=torch.Generator().manual_seed(44))
+        t = torch.tensor([0.5])
+        g = torch.tensor([4.0]) if cfg["guidance_embeds"] else None
+        img_ids, txt_ids = flux_dit.latent_image_ids(gh, gw), torch.zeros(n_txt, 3)
+        out = dict(hidden=f32(x), enc=f32(enc), pooled=f32(pooled), timestep=t.numpy(), img_ids=img_ids.numpy(),
+                   txt_ids=txt_ids.numpy(), grid=np.array([gh, gw]))
+        if g is not None:
+            out["guidance"] = g.numpy()
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            model = fm.FluxTransformer2DModel(
+                in_channels=cfg["in_channels"], num_layers=cfg["num_layers"], num_single_layers=cfg["num_single_layers"],
+                attention_head_dim=cfg["dim"] // cfg["heads"], num_attention_heads=cfg["heads"],
+                joint_attention_dim=cfg["joint_dim"], pooled_projection_dim=cfg["pooled_dim"],
+                guidance_embeds=cfg["guidance_embeds"]).eval()
+            model.load_state_dict(w32, strict=True)
+            model = model.to(dt)
+            with torch.inference_mode():
+                y = model(x.to(dt), enc.to(dt), pooled.to(dt), t.to(dt), img_ids, txt_ids, g, return_dict=False)[0]
+                out["out_" + tag] = f32(y)
+                hs = model.x_embedder(x.to(dt))
+                ts = t.to(dt) * 1000
+                temb = (model.time_text_embed(ts, pooled.to(dt)) if g is None
+                        else model.time_text_embed(ts, g.to(dt) * 1000, pooled.to(dt)))
+                ctx = model.context_embedder(enc.to(dt))
+                rope = model.pos_embed(torch.cat((txt_ids, img_ids), dim=0))
+                out["temb_" + tag] = f32(temb)
+                out["rope_cos"], out["rope_sin"] = rope[0].numpy(), rope[1].numpy()
+                ctx1, hs1 = model.transformer_blocks[0](hidden_states=hs, encoder_hidden_states=ctx, temb=temb,
+                                                        image_rotary_emb=rope)
+                out["dual0_ctx_" + tag], out["dual0_x_" + tag] = f32(ctx1), f32(hs1)
+                ctx2, hs2 = model.single_transformer_blocks[0](hidden_states=hs1, encoder_hidden_states=ctx1, temb=temb,
+                                                               image_rotary_emb=rope)
+                out["single0_ctx_" + tag], out["single0_x_" + tag] = f32(ctx2), f32(hs2)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae"]
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux"]
     for wname in which:
         fn = globals().get("golden_" + wname)
         if fn is None:

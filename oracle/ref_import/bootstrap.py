@@ -34,7 +34,8 @@ def setup():
     import src  # noqa: F401  (namespace/regular package at apps/api/src)
 
     for name in ("transformer", "vae", "scheduler", "engine", "transformer.wan", "transformer.wan.base",
-                 "vae.wan", "engine.wan"):
+                 "vae.wan", "engine.wan", "transformer.flux", "transformer.flux.base", "transformer.hunyuanvideo15",
+                 "transformer.hunyuanvideo15.base", "transformer.qwenimage", "transformer.qwenimage.base"):
         full = "src." + name
         if full in sys.modules:
             continue
@@ -42,6 +43,10 @@ def setup():
         m.__path__ = [os.path.join(REFERENCE_API, "src", *name.split("."))]
         m.__package__ = full
         sys.modules[full] = m
+    # families other than Wan import the registry from the package itself (flux/base/model.py:56)
+    tr = sys.modules["src.transformer"]
+    if not hasattr(tr, "TRANSFORMERS_REGISTRY"):
+        tr.TRANSFORMERS_REGISTRY = importlib.import_module("src.transformer.base").TRANSFORMERS_REGISTRY
 
 
 def ref(module: str):

@@ -34,6 +34,8 @@ class FeedForward(nn.Module):
 
 
 class AttentionModuleMixin:
+    fused_projections = False  # upstream class attribute (fuse_projections() flips it; never called on this path)
+
     def set_processor(self, processor):
         self.processor = processor if processor is not None else self._default_processor_cls()
 
@@ -56,3 +58,8 @@ class Attention(nn.Module):
         self.norm_k = None
         self.add_k_proj = None
         self.add_v_proj = None
+
+
+class AttentionMixin:
+    """Processor get/set helpers of upstream; the hot path never calls them."""
+    pass

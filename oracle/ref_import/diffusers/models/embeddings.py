@@ -59,3 +59,80 @@ class PixArtAlphaTextProjection(nn.Module):
 
     def forward(self, caption):
         return self.linear_2(self.act_1(self.linear_1(caption)))
+
+
+# Restated from knowledge of upstream diffusers (models/embeddings.py); call sites in the reference:
+# transformer/flux/base/model.py:339-346 (rope table), :432-440 (time/guidance/pooled-text embedding),
+# transformer/flux/base/attention.py:87-88 (apply_rotary_emb).
+class CombinedTimestepTextProjEmbeddings(nn.Module):
+    def __init__(self, embedding_dim, pooled_projection_dim):
+        super().__init__()
+        self.time_proj = Timesteps(num_channels=256, flip_sin_to_cos=True, downscale_freq_shift=0)
+        self.timestep_embedder = TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+        self.text_embedder = PixArtAlphaTextProjection(pooled_projection_dim, embedding_dim, act_fn="silu")
+
+    def forward(self, timestep, pooled_projection):
+        timesteps_proj = self.time_proj(timestep)
+        timesteps_emb = self.timestep_embedder(timesteps_proj.to(dtype=pooled_projection.dtype))
+        pooled_projections = self.text_embedder(pooled_projection)
+        return timesteps_emb + pooled_projections
+
+
+class CombinedTimestepGuidanceTextProjEmbeddings(nn.Module):
+    def __init__(self, embedding_dim, pooled_projection_dim):
+        super().__init__()
+        self.time_proj = Timesteps(num_channels=256, flip_sin_to_cos=True, downscale_freq_shift=0)
+        self.timestep_embedder = TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+        self.guidance_embedder = TimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+        self.text_embedder = PixArtAlphaTextProjection(pooled_projection_dim, embedding_dim, act_fn="silu")
+
+    def forward(self, timestep, guidance, pooled_projection):
+        timesteps_proj = self.time_proj(timestep)
+        timesteps_emb = self.timestep_embedder(timesteps_proj.to(dtype=pooled_projection.dtype))
+        guidance_proj = self.time_proj(guidance)
+        guidance_emb = self.guidance_embedder(guidance_proj.to(dtype=pooled_projection.dtype))
+        time_guidance_emb = timesteps_emb + guidance_emb
+        pooled_projections = self.text_embedder(pooled_projection)
+        return time_guidance_emb + pooled_projections
+
+
+def get_1d_rotary_pos_embed(dim, pos, theta=10000.0, use_real=False, linear_factor=1.0, ntk_factor=1.0,
+                            repeat_interleave_real=True, freqs_dtype=torch.float32):
+    assert dim % 2 == 0
+    if isinstance(pos, int):
+        pos = torch.arange(pos)
+    theta = theta * ntk_factor
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=freqs_dtype, device=pos.device)[: (dim // 2)] / dim))
+    freqs = freqs / linear_factor
+    freqs = torch.outer(pos, freqs)
+    if use_real and repeat_interleave_real:
+        freqs_cos = freqs.cos().repeat_interleave(2, dim=1).float()
+        freqs_sin = freqs.sin().repeat_interleave(2, dim=1).float()
+        return freqs_cos, freqs_sin
+    if use_real:
+        freqs_cos = torch.cat([freqs.cos(), freqs.cos()], dim=-1).float()
+        freqs_sin = torch.cat([freqs.sin(), freqs.sin()], dim=-1).float()
+        return freqs_cos, freqs_sin
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+def apply_rotary_emb(x, freqs_cis, use_real=True, use_real_unbind_dim=-1, sequence_dim=2):
+    if not use_real:
+        raise NotImplementedError
+    cos, sin = freqs_cis
+    if sequence_dim == 2:
+        cos, sin = cos[None, None, :, :], sin[None, None, :, :]
+    elif sequence_dim == 1:
+        cos, sin = cos[None, :, None, :], sin[None, :, None, :]
+    else:
+        raise ValueError(sequence_dim)
+    cos, sin = cos.to(x.device), sin.to(x.device)
+    if use_real_unbind_dim == -1:
+        x_real, x_imag = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+        x_rotated = torch.stack([-x_imag, x_real], dim=-1).flatten(3)
+    elif use_real_unbind_dim == -2:
+        x_real, x_imag = x.reshape(*x.shape[:-1], 2, -1).unbind(-2)
+        x_rotated = torch.cat([-x_imag, x_real], dim=-1)
+    else:
+        raise ValueError(use_real_unbind_dim)
+    return (x.float() * cos + x_rotated.float() * sin).to(x.dtype)

@@ -12,3 +12,57 @@ class FP32LayerNorm(torch.nn.LayerNorm):
             self.bias.float() if self.bias is not None else None,
             self.eps,
         ).to(origin_dtype)
+
+
+# The three adaptive norms below restate upstream diffusers (models/normalization.py) from knowledge of the
+# published code; the reference instantiates them at transformer/flux/base/model.py:183,247-248,451.
+class AdaLayerNormZero(torch.nn.Module):
+    def __init__(self, embedding_dim, num_embeddings=None, norm_type="layer_norm", bias=True):
+        super().__init__()
+        assert num_embeddings is None
+        self.emb = None
+        self.silu = torch.nn.SiLU()
+        self.linear = torch.nn.Linear(embedding_dim, 6 * embedding_dim, bias=bias)
+        if norm_type == "layer_norm":
+            self.norm = torch.nn.LayerNorm(embedding_dim, elementwise_affine=False, eps=1e-6)
+        elif norm_type == "fp32_layer_norm":
+            self.norm = FP32LayerNorm(embedding_dim, elementwise_affine=False, bias=False)
+        else:
+            raise ValueError(norm_type)
+
+    def forward(self, x, timestep=None, class_labels=None, hidden_dtype=None, emb=None):
+        emb = self.linear(self.silu(emb))
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
+        x = self.norm(x) * (1 + scale_msa[:, None]) + shift_msa[:, None]
+        return x, gate_msa, shift_mlp, scale_mlp, gate_mlp
+
+
+class AdaLayerNormZeroSingle(torch.nn.Module):
+    def __init__(self, embedding_dim, norm_type="layer_norm", bias=True):
+        super().__init__()
+        self.silu = torch.nn.SiLU()
+        self.linear = torch.nn.Linear(embedding_dim, 3 * embedding_dim, bias=bias)
+        assert norm_type == "layer_norm"
+        self.norm = torch.nn.LayerNorm(embedding_dim, elementwise_affine=False, eps=1e-6)
+
+    def forward(self, x, emb=None):
+        emb = self.linear(self.silu(emb))
+        shift_msa, scale_msa, gate_msa = emb.chunk(3, dim=1)
+        x = self.norm(x) * (1 + scale_msa[:, None]) + shift_msa[:, None]
+        return x, gate_msa
+
+
+class AdaLayerNormContinuous(torch.nn.Module):
+    def __init__(self, embedding_dim, conditioning_embedding_dim, elementwise_affine=True, eps=1e-5, bias=True,
+                 norm_type="layer_norm"):
+        super().__init__()
+        self.silu = torch.nn.SiLU()
+        self.linear = torch.nn.Linear(conditioning_embedding_dim, embedding_dim * 2, bias=bias)
+        assert norm_type == "layer_norm"
+        self.norm = torch.nn.LayerNorm(embedding_dim, eps, elementwise_affine, bias)
+
+    def forward(self, x, conditioning_embedding):
+        emb = self.linear(self.silu(conditioning_embedding).to(x.dtype))
+        scale, shift = torch.chunk(emb, 2, dim=1)
+        x = self.norm(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+        return x
