@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Secondary benchmark (BASELINE.json configs[1]): FLUX.1-dev t2i 1024x1024, bf16, one denoise step = one DiT forward
+(guidance-distilled, no CFG) + the flow-match Euler update, on ONE B200.  The headline metric of the repository stays
+bench.py (Wan-2.2); this script reports the same quantities for the Flux path:
+
+    python scripts/bench_flux.py [--steps K] [--warmup W] [--graph] [--layers 19 --single-layers 38]
+
+Prints one JSON line: steps/s with inputs resident (CUDA events), the algorithmic TFLOP/s against the measured bf16 peak,
+an end-to-end figure from pinned host buffers (H2D of the packed latents + text embeddings, D2H of the new latents inside
+the timed region) and, with --graph, the same step replayed from a CUDA graph (f1: launch-bound inner loop captured).
+Synthetic inputs and random-init weights of the FLUX.1-dev architecture (23.8 GB bf16).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+S_IMG, S_TXT, DIM, HEADS = 4096, 512, 3072, 24
+
+
+def flops_forward(layers: int, single: int) -> float:
+    s = S_IMG + S_TXT
+    per_block = 24.0 * s * DIM * DIM + 4.0 * s * s * DIM   # dual: (6+2+16) S d^2, single: (6+8+10) S d^2; attention 4 S^2 d
+    return (layers + single) * per_block
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--layers", type=int, default=19)
+    ap.add_argument("--single-layers", type=int, default=38)
+    ap.add_argument("--graph", action="store_true")
+    a = ap.parse_args()
+
+    from apex_studio_b200 import ops
+    from apex_studio_b200.flux import FluxConfig, FluxTransformer2DModel
+    from apex_studio_b200.scheduler import FlowMatchEulerDiscreteScheduler, calculate_shift
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    m = FluxTransformer2DModel(FluxConfig(num_layers=a.layers, num_single_layers=a.single_layers, guidance_embeds=True))
+    m.init_random_weights(dev)
+    gen = torch.Generator().manual_seed(42)
+    lat_h = torch.randn(1, S_IMG, 64, generator=gen).bfloat16().pin_memory()
+    enc_h = torch.randn(1, S_TXT, 4096, generator=gen).bfloat16().pin_memory()
+    pooled_h = torch.randn(1, 768, generator=gen).bfloat16().pin_memory()
+    out_h = torch.empty(1, S_IMG, 64, dtype=torch.bfloat16).pin_memory()
+    ids = torch.zeros(64, 64, 3)
+    ids[..., 1] += torch.arange(64)[:, None]
+    ids[..., 2] += torch.arange(64)[None, :]
+    img_ids, txt_ids = ids.reshape(-1, 3), torch.zeros(S_TXT, 3)
+    guidance = torch.full([1], 3.5, device=dev)
+    n_sched = 28
+    sch = FlowMatchEulerDiscreteScheduler()
+    ts = sch.set_timesteps(n_sched, device=dev, sigmas=np.linspace(1.0, 1 / n_sched, n_sched), mu=calculate_shift(S_IMG))
+
+    lat, enc, pooled = lat_h.to(dev), enc_h.to(dev), pooled_h.to(dev)
+
+    def step(i, x):
+        t = ts[i % n_sched]
+        pred = m(x, enc, pooled, (t.expand(1).to(x.dtype)) / 1000, img_ids, txt_ids, guidance, return_dict=False)[0]
+        sch._step_index = i % n_sched
+        return sch.step(pred, t, x)[0]
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    x = lat
+    for i in range(a.warmup):
+        x = step(i, x)
+    ops.launch_count = 0
+    state = {"x": lat}
+
+    def resident(i):
+        state["x"] = step(i, state["x"])
+
+    ms = timed(resident, a.steps)
+    launches = ops.launch_count // a.steps
+
+    def e2e(i):
+        xd = lat_h.to(dev, non_blocking=True)
+        ed = enc_h.to(dev, non_blocking=True)
+        pd = pooled_h.to(dev, non_blocking=True)
+        t = ts[i % n_sched]
+        pred = m(xd, ed, pd, (t.expand(1).to(xd.dtype)) / 1000, img_ids, txt_ids, guidance, return_dict=False)[0]
+        sch._step_index = i % n_sched
+        out_h.copy_(sch.step(pred, t, xd)[0], non_blocking=True)
+
+    ms_e2e = timed(e2e, a.steps)
+    fl = flops_forward(a.layers, a.single_layers)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = peaks.get("bf16_tflops_sustained", 1376.1)
+    res = {"metric": "denoise_steps_per_sec", "workload": "FLUX.1-dev t2i 1024x1024 (4096 image + 512 text tokens, 19 + 38 blocks), "
+           "1 forward + flow-match Euler per step", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": a.steps,
+           "warmup": a.warmup, "dtype": "bf16", "data": "synthetic", "layers": [a.layers, a.single_layers],
+           "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / peak, "peak": peak,
+           "gpu_launches_per_step": launches,
+           "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": (lat_h.numel() + enc_h.numel() + pooled_h.numel()) * 2, "d2h_bytes_per_step": out_h.numel() * 2},
+           "seconds_per_image_28_steps": 28 * ms / 1000.0, "parameter_gb": m.parameter_bytes() / 1e9}
+
+    if a.graph:
+        # static buffers; the forward + Euler update of one timestep replayed from a CUDA graph
+        xs = lat.clone()
+        tval = (ts[3].expand(1).to(xs.dtype)) / 1000
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                m(xs, enc, pooled, tval, img_ids, txt_ids, guidance, return_dict=False)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            pred = m(xs, enc, pooled, tval, img_ids, txt_ids, guidance, return_dict=False)[0]
+            sch._step_index = 3
+            y = sch.step(pred, ts[3], xs)[0]
+        eager = m(xs, enc, pooled, tval, img_ids, txt_ids, guidance, return_dict=False)[0]
+        g.replay()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(eager, pred))
+        ms_g = timed(lambda i: g.replay(), a.steps)
+        res["cuda_graph"] = {"value": 1000.0 / ms_g, "ms_per_step": ms_g, "tflops": fl / ms_g / 1e9,
+                             "frac_of_peak": fl / ms_g / 1e9 / peak, "bit_identical_to_eager": same}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
