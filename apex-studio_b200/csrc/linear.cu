@@ -200,6 +200,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (p.epi == B200_EPI_GELU_TANH) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        } else if (p.epi == B200_EPI_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+        } else if (p.epi == B200_EPI_GELU_ERF) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
         }
         if (p.epi == B200_EPI_BIAS_F32) {
           if (row_ok) {
@@ -293,7 +299,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   if (!A || !W || !C) return B200_ERR_ARG;
   const int bias_row = (epilogue & B200_EPI_ROW_BIAS) ? 1 : 0;
   epilogue &= ~B200_EPI_ROW_BIAS;
-  if (epilogue < 0 || epilogue > 3) return B200_ERR_ARG;
+  if (epilogue < 0 || epilogue > 5) return B200_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return B200_ERR_SHAPE;
   if ((K % 8) || (lda % 8) || (ldw % 8)) return B200_ERR_ALIGN;
   if (epilogue == B200_EPI_BIAS_F32 ? (ldc % 4) : (ldc % 8)) return B200_ERR_ALIGN;

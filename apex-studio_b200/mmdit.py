@@ -1,0 +1,91 @@
+"""Dual-stream (MMDiT) transformer block on the B200 kernels, shared by the HunyuanVideo-1.5 and QwenImage host mirrors
+(the Flux mirror in flux/model.py predates this helper and keeps its own copy of the sequence).
+
+The three reference blocks -- ``HunyuanVideo15TransformerBlock.forward`` (transformer/hunyuanvideo15/base/model.py:617-694),
+``QwenImageTransformerBlock.forward`` (transformer/qwenimage/base/model.py:679-750), ``FluxTransformerBlock.forward``
+(transformer/flux/base/model.py:257-328) -- are the same computation on two token streams that meet in one joint attention:
+
+    per stream:  LayerNorm (no affine) * (1 + scale_msa) + shift_msa  ->  fused q|k|v projection  ->  per-head RMS-norm (+ RoPE)
+    joint:       attention over the concatenated sequence (no mask)
+    per stream:  h += gate_msa * out_proj(attn);  LayerNorm * (1 + scale_mlp) + shift_mlp;  h += gate_mlp * FF_gelu_tanh(.)
+
+They differ in the order of the streams inside the joint sequence, in which streams are rotated, and in the rounding points
+of the per-head norm (``norm_mode`` of ``ops.headnorm_rope_``).  Here ONE residual stream ``h [S_a + S_b, dim]`` holds both
+streams as row ranges in the reference's concatenation order, so no concat / split copy exists: the fused QKV GEMMs write
+the row ranges of one ``[S, 3*dim]`` buffer, the attention kernel reads q|k|v as strided column blocks through TMA and
+writes ``[S, dim]``, and both gate * y + residual updates are GEMM epilogues (12 GEMM-class + 5 row-kernel launches).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+
+class JointWorkspace:
+    """Activation buffers of one forward, shared by all blocks (token-major bf16)."""
+
+    def __init__(self, tokens: int, dim: int, ffn_dim: int, device):
+        bf = torch.bfloat16
+        self.tokens, self.dim, self.ffn_dim = tokens, dim, ffn_dim
+        self.h = torch.empty(tokens, dim, dtype=bf, device=device)       # residual stream, both streams
+        self.norm = torch.empty(tokens, dim, dtype=bf, device=device)
+        self.qkv = torch.empty(tokens, 3 * dim, dtype=bf, device=device)
+        self.attn = torch.empty(tokens, dim, dtype=bf, device=device)
+        self.ffn = torch.empty(tokens, ffn_dim, dtype=bf, device=device)
+
+
+@dataclass
+class StreamParams:
+    """One stream of one block: its row range in the joint buffers, the six modulation vectors in the reference's chunk
+    order (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), weight-key prefixes and its RoPE rows."""
+    rows: slice
+    mod: Sequence[torch.Tensor]
+    qkv: str
+    norm_q: str
+    norm_k: str
+    out: str
+    ff: str
+    rope: Optional[torch.Tensor]
+
+
+def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: Sequence[StreamParams], heads: int,
+                      norm_mode: int, eps: float = 1e-6) -> None:
+    """One dual-stream block in place on ``ws.h``; see the module docstring."""
+    d = ws.dim
+    for s in streams:
+        shift_msa, scale_msa = s.mod[0], s.mod[1]
+        ops.adaln_zero_modulate(ws.h[s.rows], scale_msa, shift_msa, eps=eps, out=ws.norm[s.rows])
+        ops.linear(ws.norm[s.rows], w[s.qkv + ".weight"], w.get(s.qkv + ".bias"), out=ws.qkv[s.rows])
+        ops.headnorm_rope_(ws.qkv[s.rows, :d], ws.qkv[s.rows, d:2 * d], w[s.norm_q], w[s.norm_k], s.rope, heads, eps, norm_mode)
+    S = ws.tokens
+    as4 = lambda t: t.view(1, S, heads, 128).transpose(1, 2)
+    ops.attention(as4(ws.qkv[:, :d]), as4(ws.qkv[:, d:2 * d]), as4(ws.qkv[:, 2 * d:]), out=as4(ws.attn))
+    for s in streams:
+        gate_msa, shift_mlp, scale_mlp, gate_mlp = s.mod[2], s.mod[3], s.mod[4], s.mod[5]
+        h = ws.h[s.rows]
+        ops.linear(ws.attn[s.rows], w[s.out + ".weight"], w.get(s.out + ".bias"), epilogue=ops.EPI_GATE_RES, out=h,
+                   gate=gate_msa)
+        ops.adaln_zero_modulate(h, scale_mlp, shift_mlp, eps=eps, out=ws.norm[s.rows])
+        ops.mlp_gelu_(h, ws.norm[s.rows], w[s.ff + ".net.0.proj.weight"], w.get(s.ff + ".net.0.proj.bias"),
+                      w[s.ff + ".net.2.weight"], w.get(s.ff + ".net.2.bias"), gate_mlp, ws.ffn)
+
+
+def fuse_linears(w: Dict[str, torch.Tensor], dst: str, srcs: Sequence[str]) -> None:
+    """Concatenate nn.Linear weights (and biases) row-wise under a new key, removing the sources."""
+    w[dst + ".weight"] = torch.cat([w.pop(s + ".weight") for s in srcs], dim=0).contiguous()
+    if all((s + ".bias") in w for s in srcs):
+        w[dst + ".bias"] = torch.cat([w.pop(s + ".bias") for s in srcs], dim=0).contiguous()
+
+
+def sinusoid_256(t: torch.Tensor, device) -> torch.Tensor:
+    """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): fp32 [cos | sin] of t * 10000^(-i/128)."""
+    import math
+
+    half = 128
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=device) / half)
+    arg = t[:, None].float() * freqs[None, :]
+    return torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_GELU_TANH, EPI_GATE_RES, EPI_BIAS_F32 = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU_TANH, EPI_GATE_RES, EPI_BIAS_F32, EPI_SILU, EPI_GELU_ERF = 0, 1, 2, 3, 4, 5
 
 #: number of kernels launched through this module since import / last reset (bench.py's gpu_launches)
 launch_count = 0

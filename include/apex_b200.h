@@ -65,6 +65,8 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, i
 #define B200_EPI_GELU_TANH 1
 #define B200_EPI_GATE_RES 2
 #define B200_EPI_BIAS_F32 3
+#define B200_EPI_SILU 4     /* C = silu(acc + bias): FeedForward("linear-silu"), hunyuanvideo15/base/model.py:545-550 */
+#define B200_EPI_GELU_ERF 5 /* C = gelu(acc + bias), exact erf form: nn.GELU(), hunyuanvideo15/base/model.py:571,589 */
 /* OR-ed into `epilogue`: bias is indexed by ROW ([M]) instead of by column -- used for transposed projections
  * (V^T = W_v x^T + b_v of the VAE mid-block attention, vae/wan/model.py:470-478). */
 #define B200_EPI_ROW_BIAS 16

@@ -225,9 +225,66 @@ def golden_flux():
         print(name, {k: v.shape for k, v in out.items()})
 
 
+HY15_CONFIGS = {
+    # name: (oracle make_weights kwargs, latent shape, (text len, valid), (byt5 len, valid), image tokens, i2v?)
+    "hy15_t2v": (dict(dim=256, heads=2, num_layers=2, num_refiner_layers=2, in_channels=9, out_channels=4, text_dim=48,
+                      text2_dim=40, image_dim=24, byt5_hidden=64), (1, 9, 3, 4, 6), (10, 7), (6, 4), 5, False),
+    "hy15_i2v": (dict(dim=256, heads=2, num_layers=1, num_refiner_layers=1, in_channels=9, out_channels=4, text_dim=48,
+                      text2_dim=40, image_dim=24, byt5_hidden=64), (1, 9, 5, 8, 10), (12, 12), (6, 3), 5, True),
+}
+
+
+def build_reference_hy15(cfg, w32):
+    hm = bootstrap.ref("src.transformer.hunyuanvideo15.base.model")
+    model = hm.HunyuanVideo15Transformer3DModel(
+        in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], num_attention_heads=cfg["heads"],
+        attention_head_dim=cfg["dim"] // cfg["heads"], num_layers=cfg["num_layers"],
+        num_refiner_layers=cfg["num_refiner_layers"], text_embed_dim=cfg["text_dim"], text_embed_2_dim=cfg["text2_dim"],
+        image_embed_dim=cfg["image_dim"], patch_size=1, patch_size_t=1).eval()
+    # the reference hard-codes the ByT5 projection width to 2048 (model.py:856-858); the fixture keeps it small
+    model.context_embedder_2 = hm.HunyuanVideo15ByT5TextProjection(cfg["text2_dim"], cfg["byt5_hidden"], cfg["dim"]).eval()
+    model.load_state_dict(w32, strict=True)
+    return model
+
+
+def golden_hy15():
+    """Reference HunyuanVideo15Transformer3DModel with the `sdpa` backend, fp32 and bf16: final output plus the reordered
+    condition tokens and the first dual-stream block.  Text masks with padding (valid prefix) exercise the refiner's
+    key-padding mask and the valid-first token reorder; t2v = all-zero image embeds, i2v = random image embeds."""
+    import hy15_dit
+
+    a = bootstrap.ref("src.attention.functions")
+    a.attention_register.set_default("sdpa")
+    for name, (cfg, lshape, (l1, v1), (l2, v2), l3, i2v) in HY15_CONFIGS.items():
+        w32 = hy15_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+        x = torch.randn(lshape, generator=torch.Generator().manual_seed(42))
+        text = torch.randn(1, l1, cfg["text_dim"], generator=torch.Generator().manual_seed(43))
+        text2 = torch.randn(1, l2, cfg["text2_dim"], generator=torch.Generator().manual_seed(44))
+        img = torch.randn(1, l3, cfg["image_dim"], generator=torch.Generator().manual_seed(45)) if i2v else torch.zeros(1, l3, cfg["image_dim"])
+        m1, m2 = torch.zeros(1, l1), torch.zeros(1, l2)
+        m1[:, :v1], m2[:, :v2] = 1, 1
+        t = torch.tensor([500.0])
+        out = dict(hidden=f32(x), text=f32(text), text2=f32(text2), image=f32(img), mask=m1.numpy(), mask2=m2.numpy(),
+                   timestep=t.numpy())
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            model = build_reference_hy15(cfg, w32).to(dt)
+            with torch.inference_mode():
+                y = model(x.to(dt), t.to(dt), text.to(dt), m1, encoder_hidden_states_2=text2.to(dt),
+                          encoder_attention_mask_2=m2, image_embeds=img.to(dt), return_dict=False)[0]
+                out["out_" + tag] = f32(y)
+                temb = model.time_embed(t.to(dt))
+                out["temb_" + tag] = f32(temb)
+                ref_txt = model.context_embedder(text.to(dt), t.to(dt), m1)
+                out["refined_" + tag] = f32(ref_txt)
+                rope = model.rope(x)
+                out["rope_cos"], out["rope_sin"] = rope[0].numpy(), rope[1].numpy()
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux"]
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15"]
     for wname in which:
         fn = globals().get("golden_" + wname)
         if fn is None:

@@ -13,6 +13,17 @@ class GELU(nn.Module):
         return F.gelu(self.proj(hidden_states), approximate=self.approximate)
 
 
+class LinearActivation(nn.Module):
+    def __init__(self, dim_in, dim_out, bias=True, activation="silu"):
+        super().__init__()
+        assert activation == "silu"
+        self.proj = nn.Linear(dim_in, dim_out, bias=bias)
+        self.activation = nn.SiLU()
+
+    def forward(self, hidden_states):
+        return self.activation(self.proj(hidden_states))
+
+
 class FeedForward(nn.Module):
     def __init__(self, dim, dim_out=None, mult=4, dropout=0.0, activation_fn="geglu", final_dropout=False,
                  inner_dim=None, bias=True):
@@ -23,6 +34,8 @@ class FeedForward(nn.Module):
             act = GELU(dim, inner_dim, approximate="tanh", bias=bias)
         elif activation_fn == "gelu":
             act = GELU(dim, inner_dim, bias=bias)
+        elif activation_fn == "linear-silu":
+            act = LinearActivation(dim, inner_dim, bias=bias, activation="silu")
         else:
             raise NotImplementedError(activation_fn)
         self.net = nn.ModuleList([act, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out, bias=bias)])

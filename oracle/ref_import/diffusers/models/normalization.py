@@ -66,3 +66,32 @@ class AdaLayerNormContinuous(torch.nn.Module):
         scale, shift = torch.chunk(emb, 2, dim=1)
         x = self.norm(x) * (1 + scale)[:, None, :] + shift[:, None, :]
         return x
+
+
+class RMSNorm(torch.nn.Module):
+    """diffusers RMSNorm (restated): fp32 statistic, `x * rsqrt` promoted to fp32, cast to the weight dtype when the
+    weight is half precision, then the gain multiply (qwenimage/base/attention.py:115-122 calls it on [B,S,H,D])."""
+
+    def __init__(self, dim, eps, elementwise_affine=True, bias=False):
+        super().__init__()
+        self.eps = eps
+        self.elementwise_affine = elementwise_affine
+        if isinstance(dim, int):
+            dim = (dim,)
+        self.dim = torch.Size(dim)
+        self.weight = torch.nn.Parameter(torch.ones(dim)) if elementwise_affine else None
+        self.bias = torch.nn.Parameter(torch.zeros(dim)) if (elementwise_affine and bias) else None
+
+    def forward(self, hidden_states):
+        input_dtype = hidden_states.dtype
+        variance = hidden_states.to(torch.float32).pow(2).mean(-1, keepdim=True)
+        hidden_states = hidden_states * torch.rsqrt(variance + self.eps)
+        if self.weight is not None:
+            if self.weight.dtype in [torch.float16, torch.bfloat16]:
+                hidden_states = hidden_states.to(self.weight.dtype)
+            hidden_states = hidden_states * self.weight
+            if self.bias is not None:
+                hidden_states = hidden_states + self.bias
+        else:
+            hidden_states = hidden_states.to(input_dtype)
+        return hidden_states

@@ -1,0 +1,92 @@
+"""GPU parity tests of the HunyuanVideo-1.5 path (BASELINE.json configs[4]) through the C ABI, against
+the CPU oracle (oracle/hy15_dit.py, pinned bit-exactly to the reference's own model) and the reference's golden vectors.
+Bar for whole forwards: relative L2 vs the exact-math fp32 oracle <= max(1e-3, 1.5 x the reference's own bf16 error
+against that oracle), and <= 2e-2 vs the reference's bf16 output."""
+import os
+
+import pytest
+import torch
+
+import hy15_dit
+from test_gpu_parity import rel_l2
+from test_oracle_hy15 import CONFIGS, _product, inputs, kw, load
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(cfg, w32):
+    m = _product(cfg)
+    m.load_state_dict(w32, device=DEV)
+    return m
+
+
+def _call(m, x, t, text, mask, text2, mask2, img):
+    return m(x.to(DEV), t.to(DEV), text.to(DEV), mask, encoder_hidden_states_2=text2.to(DEV), encoder_attention_mask_2=mask2,
+             image_embeds=img.to(DEV), return_dict=False)[0]
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_hy15_forward_vs_reference_golden(name):
+    cfg, g = CONFIGS[name], load(name)
+    w32 = hy15_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+    m = _model(cfg, w32)
+    args = inputs(g, torch.bfloat16)
+    out = _call(m, *args)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == tuple(g["out_bf16"].shape)
+    exact = hy15_dit.hy15_forward(*inputs(g, torch.float32), w32, **kw(cfg))    # exact math (no fp32 aliasing quirk)
+    ref16 = torch.from_numpy(g["out_bf16"])
+    ours, theirs = rel_l2(out, exact), rel_l2(ref16, exact)
+    assert ours <= max(1e-3, 1.5 * theirs), (ours, theirs)
+    assert rel_l2(out, ref16) <= 2e-2
+    assert torch.equal(out, _call(m, *args))                                       # workspace reuse, deterministic
+
+
+def test_hy15_token_refiner_and_condition_tokens_vs_oracle():
+    """Refiner on compacted valid tokens vs the reference's masked refiner (valid rows), and the valid-first token order."""
+    name = "hy15_t2v"
+    cfg, g = CONFIGS[name], load(name)
+    w32 = hy15_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+    m = _model(cfg, w32)
+    x, t, text, mask, text2, mask2, img = inputs(g, torch.bfloat16)
+    valid = mask[0].bool()
+    got = m.token_refiner(text[0][valid].to(DEV).contiguous(), t.to(DEV))
+    exact = torch.from_numpy(g["refined_fp32"])[0][valid]
+    ref16 = torch.from_numpy(g["refined_bf16"])[0][valid]
+    assert rel_l2(got, exact) <= max(1e-3, 1.5 * rel_l2(ref16, exact)), (rel_l2(got, exact), rel_l2(ref16, exact))
+    ctx = m.condition_tokens(text[0].to(DEV), mask[0], text2[0].to(DEV), mask2[0], img[0].to(DEV), t.to(DEV))
+    x32, t32, text32, _, text2_32, _, img32 = inputs(g, torch.float32)
+    want = hy15_dit.condition_tokens(text32, mask, text2_32, mask2, img32, t32, w32, cfg["heads"], cfg["num_refiner_layers"])[0]
+    assert ctx.shape == want.shape
+    n_valid = int(mask2.sum() + mask.sum())
+    n_img = img.shape[1]
+    assert rel_l2(ctx[:n_valid], want[:n_valid]) <= 1e-2
+    assert torch.equal(ctx[n_valid:n_valid + n_img].float().cpu(), w32["cond_type_embed.weight"][2].bfloat16().float().expand(n_img, -1))
+    assert ctx[n_valid + n_img:].abs().max().item() == 0          # padded text tokens are zeros (model.py:1073-1074)
+
+
+def test_hy15_full_width_one_block_vs_exact_oracle():
+    """HunyuanVideo-1.5 widths (d = 2048, 16 x 128 heads, text 3584 / ByT5 1472 / image 1152, 65 latent channels) with one
+    dual-stream block and one refiner block on a 5 x 16 x 20 latent grid (1600 tokens) + 64 + 32 + 16 condition tokens."""
+    cfg = dict(dim=2048, heads=16, num_layers=1, num_refiner_layers=1, in_channels=65, out_channels=32, text_dim=3584,
+               text2_dim=1472, image_dim=1152, byt5_hidden=2048)
+    w32 = hy15_dit.make_weights(**cfg, seed=5, dtype=torch.float32, std=0.02)
+    from apex_studio_b200.hunyuanvideo15 import HunyuanVideo15Config, HunyuanVideo15Transformer3DModel
+
+    m = HunyuanVideo15Transformer3DModel(HunyuanVideo15Config(num_layers=1, num_refiner_layers=1))
+    m.load_state_dict(w32, device=DEV)
+    gen = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 65, 5, 16, 20, generator=gen)
+    text, text2, img = torch.randn(1, 64, 3584, generator=gen), torch.randn(1, 32, 1472, generator=gen), torch.randn(1, 16, 1152, generator=gen)
+    mask, mask2 = torch.ones(1, 64), torch.ones(1, 32)
+    mask[:, 50:], mask2[:, 20:] = 0, 0
+    t = torch.tensor([750.0])
+    out = _call(m, x.bfloat16(), t.bfloat16(), text.bfloat16(), mask, text2.bfloat16(), mask2, img.bfloat16())
+    k = dict(heads=16, num_layers=1, num_refiner_layers=1)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    exact = hy15_dit.hy15_forward(x, t, text, mask, text2, mask2, img, w32, **k)
+    bf = hy15_dit.hy15_forward(x.bfloat16(), t.bfloat16(), text.bfloat16(), mask, text2.bfloat16(), mask2, img.bfloat16(),
+                               {kk: v.bfloat16() for kk, v in w32.items()}, **k)
+    ours, theirs = rel_l2(out, exact), rel_l2(bf, exact)
+    assert torch.isfinite(out).all() and tuple(out.shape) == (1, 32, 5, 16, 20)
+    assert ours <= max(1e-3, 1.5 * theirs), (ours, theirs)
