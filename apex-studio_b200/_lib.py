@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200_frames_to_uint8": (_i, [_p, _p, _i, _i, _i, _p]),
     "b200_adaln_zero_modulate": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _f, _p]),
     "b200_headnorm_rope": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _f, _i, _p]),
+    "b200_rmsnorm_rows": (_i, [_p, _p, _p, _i, _i, _i64, _i64, _f, _i, _p]),
     "b200_swiglu": (_i, [_p, _p, _i, _i, _i64, _i64, _p]),
     "b200_ln_modulate": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "b200_qkv_rmsnorm_rope": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i64, _f, _p]),

@@ -125,6 +125,58 @@ swiglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y
   }
 }
 
+
+// Row RMS-norm with gain over the whole row (text-stream input norm of QwenImage: diffusers RMSNorm(joint_dim),
+// qwenimage/base/model.py:826,920), out of place; `mode` as in headnorm_rope.  One CTA per row; the row is read twice
+// (the second read is an L1/L2 hit) -- the text stream has a few hundred rows.
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ w,
+                    int dim, int64_t ldx, int64_t ldy, float eps, int mode) {
+  __shared__ float red[8];
+  const int64_t row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * ldy);
+  const int nchunks = dim >> 3;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < nchunks; c += 256) {
+    const uint4 u = xr[c];
+    const uint32_t v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(v[j]), b = bf16_hi(v[j]);
+      ss += a * a + b * b;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  float r = rsqrtf(tot / static_cast<float>(dim) + eps);
+  if (mode == 2) r = round_bf16(r);
+  for (int c = threadIdx.x; c < nchunks; c += 256) {
+    const uint4 u = xr[c];
+    const uint4 g = w ? __ldg(reinterpret_cast<const uint4*>(w) + c) : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    const uint32_t v[4] = {u.x, u.y, u.z, u.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16_lo(v[j]), b = bf16_hi(v[j]);
+      if (mode == 1) {
+        a = __fmul_rn(__fmul_rn(a, r), bf16_lo(gv[j]));
+        b = __fmul_rn(__fmul_rn(b, r), bf16_hi(gv[j]));
+      } else {
+        a = round_bf16(a * r) * bf16_lo(gv[j]);
+        b = round_bf16(b * r) * bf16_hi(gv[j]);
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    yr[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace mmdit
 }  // namespace b200
 
@@ -171,6 +223,19 @@ extern "C" int b200_swiglu(const void* x, void* y, int rows, int inner, int64_t 
   if (blocks > cap) blocks = cap;
   mmdit::swiglu_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), rows, inner, ldx, ldy);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_rows(const void* x, void* y, const void* w, int rows, int dim, int64_t ldx, int64_t ldy,
+                                 float eps, int norm_mode, void* stream) {
+  if (!x || !y) return B200_ERR_ARG;
+  if (norm_mode < 1 || norm_mode > 3) return B200_ERR_ARG;
+  if (rows <= 0 || dim <= 0) return B200_ERR_SHAPE;
+  if ((dim % 8) || (ldx % 8) || (ldy % 8) || !aligned16(x) || !aligned16(y) || !aligned16(w)) return B200_ERR_ALIGN;
+  mmdit::rmsnorm_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(w), dim, ldx, ldy,
+      eps, norm_mode);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -323,6 +323,30 @@ def headnorm_rope_(q: torch.Tensor, k: Optional[torch.Tensor], wq: Optional[torc
     _count()
 
 
+def rmsnorm_rows(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float = 1e-6, norm_mode: int = NORM_DIFFUSERS_RMS,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RMS-norm with gain over the last dim of x [rows, dim] (diffusers RMSNorm of the QwenImage text stream,
+    qwenimage/base/model.py:826,920); rounding points selected by ``norm_mode`` (see headnorm_rope_)."""
+    _require_cuda_bf16("x", x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [rows, dim] with a contiguous last dim")
+    rows, dim = x.shape
+    if weight is not None:
+        _require_cuda_bf16("weight", weight)
+        if weight.numel() != dim or not weight.is_contiguous():
+            raise ValueError(f"weight must be a contiguous [{dim}] gain")
+    if out is None:
+        out = torch.empty((rows, dim), dtype=x.dtype, device=x.device)
+    _require_cuda_bf16("out", out)
+    if tuple(out.shape) != (rows, dim) or out.stride(1) != 1:
+        raise ValueError(f"out must be [{rows}, {dim}] with a contiguous last dim")
+    rc = _lib.load().b200_rmsnorm_rows(x.data_ptr(), out.data_ptr(), _ptr(weight), rows, dim, x.stride(0), out.stride(0),
+                                       float(eps), norm_mode, _stream())
+    _lib.check(rc, "b200_rmsnorm_rows")
+    _count()
+    return out
+
+
 def swiglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """silu(x[:, :inner]) * x[:, inner:] (Flux2SwiGLU, flux2/base/model.py:91-105); x [rows, 2*inner]."""
     _require_cuda_bf16("x", x)

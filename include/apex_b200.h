@@ -208,6 +208,11 @@ int b200_adaln_zero_modulate(const void* x, void* y, const void* scale, const vo
 int b200_headnorm_rope(void* q, void* k, const void* wq, const void* wk, const float* rope, int rows, int heads,
                        int head_dim, int64_t ldx, float eps, int norm_mode, void* stream);
 
+/* Row RMS-norm with gain over all `dim` channels, out of place: the text-stream input norm of QwenImage (diffusers
+ * RMSNorm(joint_attention_dim), qwenimage/base/model.py:826, called :920).  norm_mode 1..3 as in b200_headnorm_rope. */
+int b200_rmsnorm_rows(const void* x, void* y, const void* w, int rows, int dim, int64_t ldx, int64_t ldy, float eps,
+                      int norm_mode, void* stream);
+
 /* SwiGLU of a fused projection: y[:, j] = bf16(bf16(silu(x[:, j])) * x[:, inner + j]), x [rows, 2*inner] (row stride
  * ldx), y [rows, inner] (row stride ldy).  Replaces Flux2SwiGLU.forward, flux2/base/model.py:91-105. */
 int b200_swiglu(const void* x, void* y, int rows, int inner, int64_t ldx, int64_t ldy, void* stream);

@@ -282,9 +282,58 @@ def golden_hy15():
         print(name, {k: v.shape for k, v in out.items()})
 
 
+QWEN_CONFIGS = {
+    # name: (oracle make_weights kwargs, img_shapes of one sample [(f, h, w), ...], text tokens)
+    "qwen_t2i": (dict(dim=256, heads=2, num_layers=2, in_channels=16, out_channels=4, joint_dim=48), [(1, 6, 8)], 9),
+    "qwen_edit": (dict(dim=256, heads=2, num_layers=1, in_channels=16, out_channels=4, joint_dim=48),
+                  [(1, 8, 10), (1, 6, 6), (1, 4, 10)], 13),          # noisy latent + two reference images (edit-plus)
+}
+
+
+def golden_qwen():
+    """Reference QwenImageTransformer2DModel with the `sdpa` backend on seeded inputs, fp32 and bf16: output, time embedding,
+    RoPE tables and the first block.  timestep 0.5 (sigma) is exact in bf16."""
+    import qwen_dit
+
+    qm = bootstrap.ref("src.transformer.qwenimage.base.model")
+    a = bootstrap.ref("src.attention.functions")
+    a.attention_register.set_default("sdpa")
+    for name, (cfg, shapes, n_txt) in QWEN_CONFIGS.items():
+        w32 = qwen_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+        n_img = sum(f * h * w_ for f, h, w_ in shapes)
+        x = torch.randn(1, n_img, cfg["in_channels"], generator=torch.Generator().manual_seed(42))
+        enc = torch.randn(1, n_txt, cfg["joint_dim"], generator=torch.Generator().manual_seed(43))
+        t = torch.tensor([0.5])
+        out = dict(hidden=f32(x), enc=f32(enc), timestep=t.numpy(), img_shapes=np.array(shapes))
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            model = qm.QwenImageTransformer2DModel(
+                patch_size=2, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], num_layers=cfg["num_layers"],
+                attention_head_dim=cfg["dim"] // cfg["heads"], num_attention_heads=cfg["heads"],
+                joint_attention_dim=cfg["joint_dim"]).eval()
+            model.load_state_dict(w32, strict=True)
+            model = model.to(dt)
+            with torch.inference_mode():
+                y = model(hidden_states=x.to(dt), encoder_hidden_states=enc.to(dt), encoder_hidden_states_mask=torch.ones(1, n_txt),
+                          timestep=t.to(dt), img_shapes=[shapes], txt_seq_lens=[n_txt], return_dict=False)[0]
+                out["out_" + tag] = f32(y)
+                hs = model.img_in(x.to(dt))
+                temb = model.time_text_embed(t.to(dt), hs)
+                out["temb_" + tag] = f32(temb)
+                vf, tf = model.pos_embed([shapes], [n_txt], device=torch.device("cpu"))
+                out["img_freqs_re"], out["img_freqs_im"] = vf.real.numpy(), vf.imag.numpy()
+                out["txt_freqs_re"], out["txt_freqs_im"] = tf.real.numpy(), tf.imag.numpy()
+                ctx = model.txt_in(model.txt_norm(enc.to(dt)))
+                out["ctx_in_" + tag] = f32(ctx)
+                c1, h1 = model.transformer_blocks[0](hidden_states=hs, encoder_hidden_states=ctx, encoder_hidden_states_mask=None,
+                                                     temb=temb, image_rotary_emb=(vf, tf))
+                out["block0_ctx_" + tag], out["block0_x_" + tag] = f32(c1), f32(h1)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15"]
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15", "qwen"]
     for wname in which:
         fn = globals().get("golden_" + wname)
         if fn is None:
