@@ -46,6 +46,9 @@ struct Params {
   int out_t_mul, out_t_off;   // destination frame = t * out_t_mul + out_t_off + (n / Csplit)
   int Csplit;                 // channels per destination frame (== Cout unless temporal interleave)
   int Cvalid;                 // number of real output channels (planar mode; <= Cout)
+  // Pre-padded input (replicate padding materialised by the producer kernel, HunyuanVideo-1.5 VAE): the input tensor is
+  // [T + pad_t, H + 2*pad_h, W + 2*pad_w, Cin] and tap coordinates are shifted by the pads; 0 = zero fill by TMA.
+  int pad_t, pad_h, pad_w;
 };
 
 template <int BK>
@@ -134,9 +137,9 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const int kt = tap / (p.KH * p.KW);
           const int kh = (tap / p.KW) % p.KH;
           const int kw = tap % p.KW;
-          const int ti = t + kt - (p.KT - 1);
-          const int hi = h0 + kh - p.KH / 2;
-          const int wi = w0 + kw - p.KW / 2;
+          const int ti = t + kt - (p.KT - 1) + p.pad_t;
+          const int hi = h0 + kh - p.KH / 2 + p.pad_h;
+          const int wi = w0 + kw - p.KW / 2 + p.pad_w;
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -298,8 +301,9 @@ int launch(const void* x, const void* wt, Params& p, cudaStream_t st) {
   using C = Cfg<BK>;
   CUtensorMap tmX, tmW;
   {
-    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.T};
-    uint64_t str[4] = {1, (uint64_t)p.Cin, (uint64_t)p.W * p.Cin, (uint64_t)p.H * p.W * p.Cin};
+    const uint64_t wi = p.W + 2 * p.pad_w, hi = p.H + 2 * p.pad_h, ti = p.T + p.pad_t;
+    uint64_t dims[4] = {(uint64_t)p.Cin, wi, hi, ti};
+    uint64_t str[4] = {1, (uint64_t)p.Cin, wi * p.Cin, hi * wi * p.Cin};
     uint32_t box[4] = {(uint32_t)BK, (uint32_t)p.BW, (uint32_t)p.BH, 1};
     int rc = make_tmap_bf16_sw(&tmX, x, 4, dims, str, box, BK == 32);
     if (rc) return rc;
@@ -328,9 +332,9 @@ int launch(const void* x, const void* wt, Params& p, cudaStream_t st) {
 }  // namespace conv
 }  // namespace b200
 
-extern "C" int b200_conv3d_cl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T,
-                              int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul,
-                              int out_t_off, int c_split, int c_valid, void* stream) {
+static int conv3d_cl_impl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T,
+                          int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul,
+                          int out_t_off, int c_split, int c_valid, int prepadded, void* stream) {
   using namespace b200;
   using namespace b200::conv;
   if (!x || !w || !out) return B200_ERR_ARG;
@@ -364,7 +368,24 @@ extern "C" int b200_conv3d_cl(const void* x, const void* w, const void* bias, co
   p.out_mode = out_mode;
   p.out_t_mul = out_t_mul; p.out_t_off = out_t_off;
   p.Csplit = c_split; p.Cvalid = c_valid;
+  p.pad_t = prepadded ? KT - 1 : 0;
+  p.pad_h = prepadded ? KH / 2 : 0;
+  p.pad_w = prepadded ? KW / 2 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (Cin % 64 == 0) return launch<64>(x, w, p, st);
   return launch<32>(x, w, p, st);
+}
+
+extern "C" int b200_conv3d_cl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T,
+                              int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul,
+                              int out_t_off, int c_split, int c_valid, void* stream) {
+  return conv3d_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, KT, KH, KW, out_mode, out_t_mul, out_t_off, c_split,
+                        c_valid, 0, stream);
+}
+
+extern "C" int b200_conv3d_cl_padded(const void* x_padded, const void* w, const void* bias, const void* residual, void* out,
+                                     int T, int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode,
+                                     int c_valid, void* stream) {
+  return conv3d_cl_impl(x_padded, w, bias, residual, out, T, H, W, Cin, Cout, KT, KH, KW, out_mode, 1, 0, Cout, c_valid, 1,
+                        stream);
 }

@@ -218,6 +218,39 @@ int b200_rmsnorm_rows(const void* x, void* y, const void* w, int rows, int dim, 
 int b200_swiglu(const void* x, void* y, int rows, int inner, int64_t ldx, int64_t ldy, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * HunyuanVideo-1.5 3D-VAE decode (vae/hunyuanvideo15/model.py).  Its causal convs pad with
+ * mode="replicate" (:72-90), which TMA zero fill cannot express: the producer kernel materialises the padded tensor
+ * (fused with the RMS-norm + SiLU that precedes the conv) and the conv runs on it without padding.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* y [T+pad_t, H+2*pad_h, W+2*pad_w, C] = replicate_pad(f(x [T,H,W,C])), f = channel RMS-norm * gamma (+ SiLU) when gamma
+ * is not NULL (HunyuanVideo15RMS_norm :93-127 + nonlinearity :366-376), identity otherwise (conv_in :708, the upsample
+ * conv :251).  Time is padded in FRONT only (causal). */
+int b200_pad_norm_silu_cl(const void* x, void* y, const void* gamma, int T, int H, int W, int C, int pad_t, int pad_h,
+                          int pad_w, int silu, void* stream);
+
+/* b200_conv3d_cl on an input that already carries its padding: x_padded [T+KT-1, H+KH-1, W+KW-1, Cin] -> out [T,H,W,Cout]
+ * (out_mode 0) or planar [c_valid, T, H, W] (out_mode 1).  Replaces HunyuanVideo15CausalConv3d.forward :86-90. */
+int b200_conv3d_cl_padded(const void* x_padded, const void* w, const void* bias, const void* residual, void* out, int T,
+                          int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int c_valid, void* stream);
+
+/* HunyuanVideo15Upsample.forward after its conv (:249-274): DCAE channel-to-space rearrangement of h [T,H,W,F*Cout]
+ * (F = 8 with temporal upsampling, first frame not doubled; else 4) plus the channel-repeated, rearranged shortcut of the
+ * conv input x [T,H,W,Cin] -> out [T',2H,2W,Cout], T' = 2T-1 or T. */
+int b200_dcae_upsample_cl(const void* h, const void* x, void* out, int T, int H, int W, int Cout, int Cin, int temporal,
+                          void* stream);
+
+/* b200_softmax_rows with the frame-causal mask of HunyuanVideo15AttnBlock (:143-165): row r sees columns
+ * [0, (r / block + 1) * block), block = H*W; masked probabilities are written as 0. */
+int b200_softmax_rows_block_causal(const float* s, void* p, int rows, int cols, int64_t lds, int64_t ldp, float scale,
+                                   int block, void* stream);
+
+/* b200_blend_tile without the final clamp (AutoencoderKLHunyuanVideo15.tiled_decode :1060-1119 does not clamp). */
+int b200_blend_tile_noclamp(void* tile, const void* up, const void* left, void* frame, int planes, int th, int tw,
+                            int up_h, int up_w, int left_h, int left_w, int blend, int crop_h, int crop_w, int y0, int x0,
+                            int OH, int OW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Composite entry points at the granularity of the reference's call sites.  Each enqueues the
  * kernels above back to back on `stream`; tensors are contiguous ([rows, dim] unless a stride is given).
  * --------------------------------------------------------------------------------------------------------- */

@@ -331,9 +331,42 @@ def golden_qwen():
         print(name, {k: v.shape for k, v in out.items()})
 
 
+HY15_VAE_CH = (128, 128, 64, 64, 32)          # decoder order; the production widths are (1024, 1024, 512, 256, 128)
+HY15_VAE_CASES = {
+    # name: (latent shape, tiling, spatial subsample stride of the stored output)
+    "untiled": ((1, 32, 3, 8, 6), False, 1),
+    "tiled": ((1, 32, 2, 14, 10), True, 2),       # 8x8-latent tiles at stride 6: 3 x 2 tiles, ragged last row / column
+}
+
+
+def golden_hy15vae():
+    """Reference AutoencoderKLHunyuanVideo15 (reduced widths, production tiling parameters 128 px / overlap 0.25)."""
+    import hy15_vae
+
+    vm = bootstrap.ref("src.vae.hunyuanvideo15.model")
+    w32 = hy15_vae.make_weights(HY15_VAE_CH, seed=7)
+    out = {}
+    for name, (shape, tiling, sub) in HY15_VAE_CASES.items():
+        lat = torch.randn(shape, generator=torch.Generator().manual_seed(11))
+        out[name + "_latents"] = f32(lat)
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            vae = vm.AutoencoderKLHunyuanVideo15(latent_channels=32, block_out_channels=tuple(reversed(HY15_VAE_CH))).eval()
+            missing, unexpected = vae.load_state_dict(w32, strict=False)
+            assert not unexpected and all(k.startswith("encoder.") for k in missing), (missing[:3], unexpected[:3])
+            vae = vae.to(dt)
+            if tiling:
+                vae.enable_tiling()
+            with torch.no_grad():
+                y = vae.decode(lat.to(dt), return_dict=False)[0]
+            out[f"{name}_out_{tag}"] = f32(y[..., ::sub, ::sub])
+            out[f"{name}_shape"] = np.array(y.shape)
+    np.savez_compressed(os.path.join(GOLDEN, "hy15_vae.npz"), **out)
+    print("hy15_vae", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15", "qwen"]
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15", "qwen", "hy15vae"]
     for wname in which:
         fn = globals().get("golden_" + wname)
         if fn is None:
