@@ -127,3 +127,45 @@ def flux_denoise(*, latents: torch.Tensor, timesteps: torch.Tensor, scheduler, t
         if denoise_progress_callback is not None:
             denoise_progress_callback(float(i + 1) / float(total), f"Denoise {i + 1}/{total}")
     return latents
+
+
+@torch.inference_mode()
+def hy15_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, transformer, cond_latents_concat: torch.Tensor,
+                 mask_concat: torch.Tensor, image_embeds: torch.Tensor, cond_kwargs: Dict[str, Any],
+                 uncond_kwargs: Optional[Dict[str, Any]] = None, guidance_scale: float = 6.0,
+                 do_classifier_free_guidance: bool = True, guidance_rescale: float = 0.0,
+                 denoise_progress_callback: Optional[Callable] = None, parallel: Optional[ParallelContext] = None) -> torch.Tensor:
+    """The HunyuanVideo-1.5 denoise loop (apps/api/src/engine/hunyuanvideo15/t2v.py:234-338) with the same names: per step
+    ``latent_model_input = cat([latents, cond_latents_concat, mask_concat], dim=1)`` (:239-241), the timestep in the latent
+    dtype (:243-245), the unconditional and the conditional forward (:262-289), ``uncond + g * (text - uncond)`` (:291-293)
+    and ``scheduler.step`` (:320-322).  ``cond_kwargs`` / ``uncond_kwargs`` carry ``encoder_hidden_states``,
+    ``encoder_attention_mask``, ``encoder_hidden_states_2``, ``encoder_attention_mask_2`` (:248-261).
+
+    Multi-GPU: with a CFG group of 2 each rank runs ONE branch and the [B,32,F,H,W] bf16 predictions are exchanged with a
+    single all-gather per step; inside a forward the latent tokens may be sharded over the sequence-parallel group."""
+    if guidance_rescale and guidance_rescale > 0.0:
+        raise ValueError("guidance_rescale > 0 is not implemented on the b200 path")
+    par = parallel or ParallelContext.single()
+    do_cfg = bool(do_classifier_free_guidance)
+    if do_cfg and not uncond_kwargs:
+        raise ValueError("CFG requested (guidance_scale > 1.0) but no negative prompt / negative prompt embeds were provided.")
+    total = len(timesteps)
+    for i, t in enumerate(timesteps):
+        latent_model_input = torch.cat([latents, cond_latents_concat, mask_concat], dim=1)
+        timestep = t.expand(latent_model_input.shape[0]).to(latent_model_input.dtype)
+        common = dict(hidden_states=latent_model_input, image_embeds=image_embeds, timestep=timestep, return_dict=False,
+                      parallel=par)
+        if do_cfg and par.cfg_size == 2:
+            mine = transformer(**common, **(cond_kwargs if par.cfg_rank == 0 else uncond_kwargs))[0]
+            cond, uncond = par.exchange_cfg(mine)
+            noise_pred = ops.cfg_combine(cond, uncond, float(guidance_scale))
+        elif do_cfg:
+            uncond = transformer(**common, **uncond_kwargs)[0]
+            cond = transformer(**common, **cond_kwargs)[0]
+            noise_pred = ops.cfg_combine(cond, uncond, float(guidance_scale))
+        else:
+            noise_pred = transformer(**common, **cond_kwargs)[0]
+        latents = scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+        if denoise_progress_callback is not None:
+            denoise_progress_callback(float(i + 1) / float(max(total, 1)), f"Denoising step {i + 1}/{total}")
+    return latents

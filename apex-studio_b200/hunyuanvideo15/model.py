@@ -358,7 +358,11 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
         grid = (f // pt, hh // p, ww // p)
         n_lat = grid[0] * grid[1] * grid[2]
         d, H = c.inner_dim, c.num_attention_heads
-        rope = self._rope(grid)
+        from ..parallel import ParallelContext
+        par: ParallelContext = unused.pop("parallel", None) or ParallelContext.single()
+        lo, hi = par.shard_bounds(n_lat)              # this rank's latent-token shard (the whole sequence when sp_size == 1)
+        n_loc = hi - lo
+        rope = self._rope(grid)[lo:hi]
         t = timestep.to(device=dev, dtype=bf)                     # the engine passes it in the latent dtype (t2v.py:243)
         temb = self.time_embed(t)                                 # [B, dim]
         mod_all = ops.linear(F.silu(temb), w["modulation.weight"], w["modulation.bias"])
@@ -368,10 +372,10 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
                                         t[bi:bi + 1])
             n_ctx = ctx.shape[0]
             ws = self._ws
-            if ws is None or ws.tokens != n_lat + n_ctx:
-                self._ws = ws = JointWorkspace(n_lat + n_ctx, d, int(d * c.mlp_ratio), dev)
-            ops.linear(self.patchify(x_in[bi]), w["x_embedder.proj.weight"], w["x_embedder.proj.bias"], out=ws.h[:n_lat])
-            ws.h[n_lat:].copy_(ctx)
+            if ws is None or ws.tokens != n_loc + n_ctx:
+                self._ws = ws = JointWorkspace(n_loc + n_ctx, d, int(d * c.mlp_ratio), dev)
+            ops.linear(self.patchify(x_in[bi])[lo:hi], w["x_embedder.proj.weight"], w["x_embedder.proj.bias"], out=ws.h[:n_loc])
+            ws.h[n_loc:].copy_(ctx)
             m = mod_all[bi]
             for i in range(c.num_layers):
                 pfx = f"transformer_blocks.{i}"
@@ -381,17 +385,18 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
                     return m[r0:r0 + rows].chunk(6)
 
                 streams = (
-                    StreamParams(slice(0, n_lat), mods(pfx + ".norm1.linear"), pfx + ".attn.to_qkv", pfx + ".attn.norm_q.weight",
+                    StreamParams(slice(0, n_loc), mods(pfx + ".norm1.linear"), pfx + ".attn.to_qkv", pfx + ".attn.norm_q.weight",
                                  pfx + ".attn.norm_k.weight", pfx + ".attn.to_out.0", pfx + ".ff", rope),
-                    StreamParams(slice(n_lat, None), mods(pfx + ".norm1_context.linear"), pfx + ".attn.add_qkv",
+                    StreamParams(slice(n_loc, None), mods(pfx + ".norm1_context.linear"), pfx + ".attn.add_qkv",
                                  pfx + ".attn.norm_added_q.weight", pfx + ".attn.norm_added_k.weight", pfx + ".attn.to_add_out",
                                  pfx + ".ff_context", None),
                 )
-                dual_stream_block(w, ws, streams, H, ops.NORM_INPLACE_RMS)
+                dual_stream_block(w, ws, streams, H, ops.NORM_INPLACE_RMS, par=par, n_img_total=n_lat)
             r0, rows = self._mod_rows["norm_out.linear"]
             scale, shift = m[r0:r0 + rows].chunk(2)                # AdaLayerNormContinuous: scale first
-            ops.adaln_zero_modulate(ws.h[:n_lat], scale, shift, out=ws.norm[:n_lat])
-            outs.append(ops.linear(ws.norm[:n_lat], w["proj_out.weight"], w["proj_out.bias"])[:, :self._n_out])
+            ops.adaln_zero_modulate(ws.h[:n_loc], scale, shift, out=ws.norm[:n_loc])
+            y_loc = ops.linear(ws.norm[:n_loc], w["proj_out.weight"], w["proj_out.bias"])[:, :self._n_out]
+            outs.append(par.gather_tokens(y_loc.contiguous()))
         y = torch.stack(outs, dim=0).reshape(b, grid[0], grid[1], grid[2], -1, pt, p, p).permute(0, 4, 1, 5, 2, 6, 3, 7)
         out = y.flatten(6, 7).flatten(4, 5).flatten(2, 3)
         if return_dict:

@@ -53,17 +53,32 @@ class StreamParams:
 
 
 def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: Sequence[StreamParams], heads: int,
-                      norm_mode: int, eps: float = 1e-6) -> None:
-    """One dual-stream block in place on ``ws.h``; see the module docstring."""
+                      norm_mode: int, eps: float = 1e-6, par=None, n_img_total: int = 0) -> None:
+    """One dual-stream block in place on ``ws.h``; see the module docstring.
+
+    Sequence parallel (``par.sp_size > 1``): ``streams[0]`` (the image / latent stream) holds only this rank's token shard
+    (``n_img_total`` tokens over the whole group), ``streams[1]`` (text) is replicated; everything but the joint attention
+    is token-local, and the attention runs Ulysses-style on this rank's heads over ALL tokens
+    (``ParallelContext.joint_tokens_to_heads`` / ``joint_heads_to_tokens``).  Exact -- no windowing."""
     d = ws.dim
     for s in streams:
         shift_msa, scale_msa = s.mod[0], s.mod[1]
         ops.adaln_zero_modulate(ws.h[s.rows], scale_msa, shift_msa, eps=eps, out=ws.norm[s.rows])
         ops.linear(ws.norm[s.rows], w[s.qkv + ".weight"], w.get(s.qkv + ".bias"), out=ws.qkv[s.rows])
         ops.headnorm_rope_(ws.qkv[s.rows, :d], ws.qkv[s.rows, d:2 * d], w[s.norm_q], w[s.norm_k], s.rope, heads, eps, norm_mode)
-    S = ws.tokens
-    as4 = lambda t: t.view(1, S, heads, 128).transpose(1, 2)
-    ops.attention(as4(ws.qkv[:, :d]), as4(ws.qkv[:, d:2 * d]), as4(ws.qkv[:, 2 * d:]), out=as4(ws.attn))
+    if par is not None and par.sp_size > 1:
+        img, txt = streams[0], streams[1]
+        img_first = (img.rows.start or 0) == 0
+        qkv_h = par.joint_tokens_to_heads(ws.qkv, img.rows, txt.rows, heads, 128, img_first)   # [3, S_joint, (H/P)*128]
+        Sj, hp = qkv_h.shape[1], heads // par.sp_size
+        o_h = torch.empty_like(qkv_h[0])
+        as4 = lambda t: t.view(1, Sj, hp, 128).transpose(1, 2)
+        ops.attention(as4(qkv_h[0]), as4(qkv_h[1]), as4(qkv_h[2]), out=as4(o_h))
+        par.joint_heads_to_tokens(o_h, n_img_total, img_first, ws.attn, img.rows, txt.rows)
+    else:
+        S = ws.tokens
+        as4 = lambda t: t.view(1, S, heads, 128).transpose(1, 2)
+        ops.attention(as4(ws.qkv[:, :d]), as4(ws.qkv[:, d:2 * d]), as4(ws.qkv[:, 2 * d:]), out=as4(ws.attn))
     for s in streams:
         gate_msa, shift_mlp, scale_mlp, gate_mlp = s.mod[2], s.mod[3], s.mod[4], s.mod[5]
         h = ws.h[s.rows]

@@ -141,6 +141,41 @@ class ParallelContext:
         dist.all_gather_into_tensor(full, local, group=self.sp_group)
         return full
 
+    # ------------------------------------------------------------------------------------ dual-stream (MMDiT) families
+    def joint_tokens_to_heads(self, qkv_local: torch.Tensor, img_rows: slice, txt_rows: slice, heads: int, head_dim: int,
+                              img_first: bool) -> torch.Tensor:
+        """Dual-stream blocks (mmdit.dual_stream_block): the IMAGE / latent stream is token-sharded over the sp group, the
+        short text stream is replicated on every rank.  ``qkv_local`` [n_img_local + n_txt, 3*H*Dh] holds my image rows
+        and ALL text rows.  Returns [3, S_img + n_txt, (H/P)*Dh] -- all image tokens (Ulysses all-to-all) and all text
+        tokens (a local column slice: the text q|k|v of my heads were computed here) of MY heads, concatenated in the
+        reference's order (image first for HunyuanVideo-1.5, text first for Flux / QwenImage)."""
+        P = self.sp_size
+        hp = heads // P
+        if heads % P:
+            raise ValueError(f"{heads} heads are not divisible by the sequence-parallel size {P}")
+        w = hp * head_dim
+        img = self.tokens_to_heads(qkv_local[img_rows], heads, head_dim)                  # [3, S_img, w]
+        n_txt = qkv_local[txt_rows].shape[0]
+        txt = qkv_local[txt_rows].reshape(n_txt, 3, heads, head_dim)[:, :, self.sp_rank * hp:(self.sp_rank + 1) * hp]
+        txt = txt.reshape(n_txt, 3, w).permute(1, 0, 2)                                   # [3, n_txt, w]
+        return torch.cat([img, txt] if img_first else [txt, img], dim=1).contiguous()
+
+    def joint_heads_to_tokens(self, o_heads: torch.Tensor, n_img_total: int, img_first: bool, out: torch.Tensor,
+                              img_rows: slice, txt_rows: slice) -> None:
+        """Inverse of ``joint_tokens_to_heads`` for the attention output [S_img + n_txt, (H/P)*Dh]: image rows go back to
+        their token owners (all-to-all) into ``out[img_rows]``; the text rows of all head groups are all-gathered so that
+        every rank continues the replicated text stream with the full ``out[txt_rows]`` [n_txt, H*Dh]."""
+        P = self.sp_size
+        S, w = o_heads.shape
+        n_txt = S - n_img_total
+        img = o_heads[:n_img_total] if img_first else o_heads[n_txt:]
+        txt = o_heads[n_img_total:] if img_first else o_heads[:n_txt]
+        self.heads_to_tokens(img, out=out[img_rows])
+        txt = txt.contiguous()
+        allt = torch.empty((P * n_txt, w), dtype=txt.dtype, device=txt.device)      # concatenated along dim 0 (gloo-compatible)
+        dist.all_gather_into_tensor(allt, txt, group=self.sp_group)
+        out[txt_rows].copy_(allt.view(P, n_txt, w).permute(1, 0, 2).reshape(n_txt, P * w))
+
     # ------------------------------------------------------------------------------------ frames
     def allgather_frames(self, mine: torch.Tensor) -> torch.Tensor:
         """Single all-gather over ALL ranks of equally shaped per-rank tile stacks -> [world, ...]."""

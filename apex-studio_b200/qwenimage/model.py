@@ -247,17 +247,22 @@ class QwenImageTransformer2DModel(LoraHostMixin):
         txt_len = max(txt_seq_lens) if txt_seq_lens else n_txt
         if txt_len != n_txt:
             raise ValueError(f"max(txt_seq_lens) = {txt_len} must equal the text sequence length {n_txt}")
+        from ..parallel import ParallelContext
+        par: ParallelContext = unused.pop("parallel", None) or ParallelContext.single()
+        lo, hi = par.shard_bounds(n_img)              # this rank's image-token shard (everything when sp_size == 1)
+        n_loc = hi - lo
         img_rope, txt_rope = self._rope(shapes, txt_len)
+        img_rope = img_rope[lo:hi]
         temb = self.time_embed(timestep.to(device=dev, dtype=bf))
         mod_all = ops.linear(F.silu(temb), w["modulation.weight"], w["modulation.bias"])
         ws = self._ws
-        if ws is None or ws.tokens != n_txt + n_img:
-            self._ws = ws = JointWorkspace(n_txt + n_img, d, 4 * d, dev)
+        if ws is None or ws.tokens != n_txt + n_loc:
+            self._ws = ws = JointWorkspace(n_txt + n_loc, d, 4 * d, dev)
         outs = []
         for bi in range(b):
             ops.linear(ops.rmsnorm_rows(enc[bi], w["txt_norm.weight"], 1e-6, ops.NORM_DIFFUSERS_RMS), w["txt_in.weight"],
                        w["txt_in.bias"], out=ws.h[:n_txt])
-            ops.linear(x_in[bi], w["img_in.weight"], w["img_in.bias"], out=ws.h[n_txt:])
+            ops.linear(x_in[bi, lo:hi], w["img_in.weight"], w["img_in.bias"], out=ws.h[n_txt:])
             m = mod_all[bi]
 
             def mods(name):
@@ -272,11 +277,12 @@ class QwenImageTransformer2DModel(LoraHostMixin):
                     StreamParams(slice(0, n_txt), mods(p + ".txt_mod.1"), p + ".attn.add_qkv", p + ".attn.norm_added_q.weight",
                                  p + ".attn.norm_added_k.weight", p + ".attn.to_add_out", p + ".txt_mlp", txt_rope),
                 )
-                dual_stream_block(w, ws, streams, H, ops.NORM_DIFFUSERS_RMS)
+                dual_stream_block(w, ws, streams, H, ops.NORM_DIFFUSERS_RMS, par=par, n_img_total=n_img)
             r0, rows = self._mod_rows["norm_out.linear"]
             scale, shift = m[r0:r0 + rows].chunk(2)
             ops.adaln_zero_modulate(ws.h[n_txt:], scale, shift, out=ws.norm[n_txt:])
-            outs.append(ops.linear(ws.norm[n_txt:], w["proj_out.weight"], w["proj_out.bias"])[:, :self._n_out])
+            y_loc = ops.linear(ws.norm[n_txt:], w["proj_out.weight"], w["proj_out.bias"])[:, :self._n_out]
+            outs.append(par.gather_tokens(y_loc.contiguous()))
         out = torch.stack(outs, dim=0)
         if return_dict:
             return {"sample": out}

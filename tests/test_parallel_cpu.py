@@ -122,3 +122,42 @@ def test_plan_layout_and_dealing():
     assert plan_layout(4, True) == (2, 2) and plan_layout(8, True) == (2, 4) and plan_layout(8, False) == (1, 8)
     tiles = [deal_round_robin(28, 8, r) for r in range(8)]
     assert sorted(sum(tiles, [])) == list(range(28)) and [len(t) for t in tiles] == [4, 4, 4, 4, 3, 3, 3, 3]
+
+
+# ---------------------------------------------------------------------------------------------------
+def _joint_exchange(rank, world, img_first):
+    """Dual-stream families: image stream token-sharded, text stream replicated (ParallelContext.joint_*)."""
+    from apex_studio_b200.parallel import ParallelContext
+
+    par = ParallelContext.create(use_cfg=False)
+    P = par.sp_size
+    heads, hd, n_img, n_txt = 4, 8, 24, 5
+    d = heads * hd
+    g = torch.Generator().manual_seed(9)
+    img_full = torch.randn(n_img, 3 * d, generator=g)           # same on every rank
+    txt_full = torch.randn(n_txt, 3 * d, generator=g)
+    lo, hi = par.shard_bounds(n_img)
+    n_loc = hi - lo
+    if img_first:
+        local = torch.cat([img_full[lo:hi], txt_full], dim=0)
+        img_rows, txt_rows = slice(0, n_loc), slice(n_loc, None)
+        joint = torch.cat([img_full, txt_full], dim=0)
+    else:
+        local = torch.cat([txt_full, img_full[lo:hi]], dim=0)
+        img_rows, txt_rows = slice(n_txt, None), slice(0, n_txt)
+        joint = torch.cat([txt_full, img_full], dim=0)
+    got = par.joint_tokens_to_heads(local, img_rows, txt_rows, heads, hd, img_first)       # [3, S_joint, (H/P)*hd]
+    hp = heads // P
+    for which in range(3):
+        cols = joint[:, which * d:(which + 1) * d]
+        assert torch.equal(got[which], cols[:, par.sp_rank * hp * hd:(par.sp_rank + 1) * hp * hd]), (rank, which)
+    # "attention output" for my heads = q of my heads: afterwards I must hold q (all heads) of my image rows + all text rows
+    out = torch.zeros(n_loc + n_txt, d)
+    par.joint_heads_to_tokens(got[0].contiguous(), n_img, img_first, out, img_rows, txt_rows)
+    assert torch.equal(out[img_rows], img_full[lo:hi, :d]) and torch.equal(out[txt_rows], txt_full[:, :d]), rank
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("img_first", [True, False])
+def test_dual_stream_joint_exchange(world, img_first):
+    _run(world, _joint_exchange, img_first)
