@@ -161,3 +161,80 @@ def _joint_exchange(rank, world, img_first):
 @pytest.mark.parametrize("img_first", [True, False])
 def test_dual_stream_joint_exchange(world, img_first):
     _run(world, _joint_exchange, img_first)
+
+
+def _hy15_cfg_loop(rank, world):
+    """CFG-parallel hy15_denoise on 2 ranks == the sequential uncond/cond loop of engine/hunyuanvideo15/t2v.py:234-338."""
+    import numpy as np
+
+    import wan_dit
+    from apex_studio_b200 import denoise, ops
+    from apex_studio_b200.parallel import ParallelContext
+    from apex_studio_b200.scheduler import FlowMatchEulerDiscreteScheduler
+
+    ops.cfg_combine = lambda c, u, g: wan_dit.cfg_combine(c, u, g)   # oracle arithmetic on CPU
+    calls = []
+
+    class FakeDiT:
+        def __call__(self, hidden_states, timestep, encoder_hidden_states, image_embeds, return_dict=False, parallel=None, **kw):
+            assert hidden_states.shape[1] == 9 and timestep.dtype == hidden_states.dtype           # cat(latents, cond, mask)
+            calls.append(float(encoder_hidden_states.float().mean()))
+            e = encoder_hidden_states.float().mean()
+            y = 0.3 * hidden_states[:, :4].float() + 0.05 * torch.sin(hidden_states[:, :4].float() * 2 + e + timestep.float().view(-1, 1, 1, 1, 1) * 1e-3)
+            return (y.to(hidden_states.dtype),)
+
+    def run(par):
+        sch = FlowMatchEulerDiscreteScheduler(use_dynamic_shifting=False, shift=7.0)
+        ts = sch.set_timesteps(5, sigmas=np.linspace(1.0, 0.0, 6)[:-1])
+        lat = torch.randn(1, 4, 2, 4, 4, generator=torch.Generator().manual_seed(1)).bfloat16()
+        kw = dict(encoder_attention_mask=torch.ones(1, 3), encoder_hidden_states_2=torch.zeros(1, 2, 8), encoder_attention_mask_2=torch.ones(1, 2))
+        return denoise.hy15_denoise(timesteps=ts, latents=lat, scheduler=sch, transformer=FakeDiT(),
+                                    cond_latents_concat=torch.zeros(1, 4, 2, 4, 4).bfloat16(), mask_concat=torch.zeros(1, 1, 2, 4, 4).bfloat16(),
+                                    image_embeds=torch.zeros(1, 2, 8), cond_kwargs=dict(kw, encoder_hidden_states=torch.ones(1, 3, 8)),
+                                    uncond_kwargs=dict(kw, encoder_hidden_states=torch.zeros(1, 3, 8)), guidance_scale=6.0, parallel=par)
+
+    par = ParallelContext.create(use_cfg=True)
+    calls.clear()
+    sharded = run(par)
+    assert len(calls) == 5 and set(calls) == ({1.0} if par.cfg_rank == 0 else {0.0})      # one branch per rank
+    calls.clear()
+    single = run(ParallelContext.single())
+    assert calls[:2] == [0.0, 1.0] and len(calls) == 10                                   # uncond first, then cond (t2v.py:268-289)
+    assert sharded.dtype == torch.bfloat16 and torch.equal(sharded, single)
+    with pytest.raises(ValueError):
+        denoise.hy15_denoise(timesteps=[], latents=None, scheduler=None, transformer=None, cond_latents_concat=None, mask_concat=None,
+                             image_embeds=None, cond_kwargs={}, uncond_kwargs=None, do_classifier_free_guidance=True)
+
+
+def test_hy15_cfg_parallel_denoise_loop():
+    _run(2, _hy15_cfg_loop)
+
+
+def test_flux_denoise_loop_host_logic():
+    """flux_denoise (engine/flux/shared.py:504-620) with a fake transformer on the CPU: timestep / 1000 in the latent dtype,
+    guidance passed through, true-CFG branch order and combine, scheduler stepped once per timestep."""
+    import numpy as np
+
+    import wan_dit
+    from apex_studio_b200 import denoise, ops
+    from apex_studio_b200.scheduler import FlowMatchEulerDiscreteScheduler, calculate_shift
+
+    ops.cfg_combine = lambda c, u, g: wan_dit.cfg_combine(c, u, g)
+    seen = []
+
+    def fake(hidden_states, timestep, guidance, img_ids, pooled_projections, encoder_hidden_states, txt_ids, return_dict=False):
+        seen.append((float(timestep[0]), float(pooled_projections.mean())))
+        assert timestep.dtype == hidden_states.dtype and float(timestep[0]) <= 1.0 and float(guidance[0]) == 3.5
+        return (0.5 * hidden_states + pooled_projections.mean().to(hidden_states.dtype),)
+
+    sch = FlowMatchEulerDiscreteScheduler()
+    ts = sch.set_timesteps(4, sigmas=np.linspace(1.0, 0.25, 4), mu=calculate_shift(16))
+    lat = torch.randn(1, 16, 8, generator=torch.Generator().manual_seed(0)).bfloat16()
+    out = denoise.flux_denoise(latents=lat, timesteps=ts, scheduler=sch, transformer=fake, prompt_embeds=torch.zeros(1, 2, 4),
+                               pooled_prompt_embeds=torch.ones(1, 4), latent_ids=torch.zeros(16, 3), text_ids=torch.zeros(2, 3),
+                               guidance=torch.full([1], 3.5), negative_prompt_embeds=torch.zeros(1, 2, 4),
+                               negative_pooled_prompt_embeds=torch.zeros(1, 4), negative_text_ids=torch.zeros(2, 3),
+                               true_cfg_scale=2.0, use_cfg_guidance=True)
+    assert out.shape == lat.shape and out.dtype == torch.bfloat16 and sch.step_index == 4
+    assert len(seen) == 8 and [p for _, p in seen[:2]] == [1.0, 0.0]                    # positive branch first, then negative
+    assert seen[0][0] == pytest.approx(1.0, abs=1e-2)
