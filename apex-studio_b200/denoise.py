@@ -44,6 +44,79 @@ def select_guidance_scale(t, boundary_timestep, guidance_scale: Union[float, Seq
     return float(guidance_scale)
 
 
+class PreviewRenderer:
+    """Per-step preview decode (reference: ``render_on_step`` in the denoise loops,
+    engine/wan/shared/__init__.py:580-586 -> ``BaseEngine._render_step`` base_engine.py:2927-2943, which decodes the current
+    latents with the VAE on the denoise stream and hands PIL frames to the callback, stalling the loop for the whole decode).
+
+    Here the decode + frame hand-off (``vae.decode`` -> ``frames_to_uint8`` -> pinned host copy) is enqueued on a SIDE stream
+    that only waits for the latents of the finished step, so the next step's kernels are never blocked by host work, and the
+    callback is delivered with a uint8 ``[T, H, W, 3]`` numpy array once the copy has landed (at a later render point or at
+    ``finish()``).  ``decode_fn(latents) -> uint8 tensor [T,H,W,3]`` is injected so that any VAE of this package fits."""
+
+    def __init__(self, decode_fn: Callable[[torch.Tensor], torch.Tensor], callback: Callable, interval: int = 3):
+        if interval < 1:
+            raise ValueError("render_on_step_interval must be >= 1")
+        self.decode_fn, self.callback, self.interval = decode_fn, callback, int(interval)
+        self._side: Optional[torch.cuda.Stream] = None
+        self._pending: List = []
+        self.rendered_steps: List[int] = []
+
+    def wants(self, i: int, total: int) -> bool:
+        """The reference's condition (engine/wan/shared/__init__.py:581-584)."""
+        return ((i + 1) % self.interval == 0 or i == 0) and i != total - 1
+
+    def _deliver(self, block: bool) -> None:
+        keep = []
+        for ev, host, step in self._pending:
+            if ev is None or block or ev.query():
+                if ev is not None:
+                    ev.synchronize()
+                self.callback(host.numpy())
+            else:
+                keep.append((ev, host, step))
+        self._pending = keep
+
+    def maybe_render(self, i: int, total: int, latents: torch.Tensor) -> bool:
+        self._deliver(block=False)
+        if not self.wants(i, total):
+            return False
+        self.rendered_steps.append(i)
+        if not latents.is_cuda:                                   # host-logic tests: run inline
+            self._pending.append((None, self.decode_fn(latents).cpu(), i))
+            self._deliver(block=True)
+            return True
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        snap = latents.detach().clone()
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            frames = self.decode_fn(snap)
+            host = torch.empty(frames.shape, dtype=frames.dtype, pin_memory=True)
+            host.copy_(frames, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        snap.record_stream(self._side)
+        self._pending.append((ev, host, i))
+        return True
+
+    def finish(self) -> None:
+        self._deliver(block=True)
+
+
+def wan_preview_decode_fn(vae) -> Callable[[torch.Tensor], torch.Tensor]:
+    """latents fp32 [1,16,F,H,W] -> uint8 [T,H,W,3]: ``BaseEngine.vae_decode`` (base_engine.py:2030-2059: denormalise, cast to the
+    VAE dtype, forced tiling) followed by the frame hand-off kernel."""
+    from .vae.wan import frames_to_uint8
+
+    def fn(latents: torch.Tensor) -> torch.Tensor:
+        z = vae.denormalize_latents(latents).to(torch.bfloat16)
+        vae.enable_tiling()
+        return frames_to_uint8(vae.decode(z, return_dict=False)[0][0].contiguous())
+
+    return fn
+
+
 @torch.inference_mode()
 def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, high_noise_transformer,
                 low_noise_transformer=None, boundary_timestep=None, guidance_scale: Union[float, Sequence[float]] = 5.0,
@@ -51,8 +124,12 @@ def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, hi
                 unconditional_transformer_kwargs: Optional[Dict[str, Any]] = None, use_cfg_guidance: bool = True,
                 transformer_dtype=torch.bfloat16, extra_step_kwargs: Optional[Dict[str, Any]] = None,
                 denoise_progress_callback: Optional[Callable] = None, parallel: Optional[ParallelContext] = None,
-                trace: Optional[DenoiseTrace] = None) -> torch.Tensor:
-    """Returns the final fp32 latents.  ``low_noise_transformer=None`` gives ``base_denoise`` (single expert)."""
+                trace: Optional[DenoiseTrace] = None, render_on_step: bool = False,
+                render_on_step_callback: Optional[Callable] = None, render_on_step_interval: int = 3,
+                preview_decode_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:
+    """Returns the final fp32 latents.  ``low_noise_transformer=None`` gives ``base_denoise`` (single expert).
+    ``render_on_step`` / ``render_on_step_callback`` / ``render_on_step_interval`` keep the reference's names (:496-503);
+    ``preview_decode_fn`` (e.g. ``wan_preview_decode_fn(vae)``) supplies the decode that the engine's ``_render_step`` does."""
     transformer_kwargs = dict(transformer_kwargs or {})
     uncond_kwargs = dict(unconditional_transformer_kwargs or {})
     transformer_kwargs.pop("encoder_hidden_states_image", None)
@@ -61,6 +138,11 @@ def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, hi
     do_cfg = bool(use_cfg_guidance and uncond_kwargs)
     par = parallel or ParallelContext.single()
     total = len(timesteps)
+    preview = None
+    if render_on_step and render_on_step_callback is not None:
+        if preview_decode_fn is None:
+            raise ValueError("render_on_step needs `preview_decode_fn` (e.g. denoise.wan_preview_decode_fn(vae))")
+        preview = PreviewRenderer(preview_decode_fn, render_on_step_callback, render_on_step_interval)
     for i, t in enumerate(timesteps):
         latent_model_input = latents.to(transformer_dtype)
         timestep = t.expand(latents.shape[0])
@@ -89,8 +171,12 @@ def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, hi
             else:
                 noise_pred = cond
         latents = scheduler.step(noise_pred, t, latents, **extra_step_kwargs, return_dict=False)[0]
+        if preview is not None and par.rank == 0:
+            preview.maybe_render(i, total, latents)
         if denoise_progress_callback is not None:
             denoise_progress_callback(float(i + 1) / float(total), f"Denoising step {i + 1}/{total}")
+    if preview is not None:
+        preview.finish()
     return latents
 
 

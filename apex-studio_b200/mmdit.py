@@ -28,9 +28,11 @@ from . import ops
 class JointWorkspace:
     """Activation buffers of one forward, shared by all blocks (token-major bf16)."""
 
-    def __init__(self, tokens: int, dim: int, ffn_dim: int, device):
+    def __init__(self, tokens: int, dim: int, ffn_dim: int, device, ffn_act_dim: int = 0):
         bf = torch.bfloat16
         self.tokens, self.dim, self.ffn_dim = tokens, dim, ffn_dim
+        # SwiGLU feed-forwards (Flux2): ffn holds the fused [gate | value] projection, ffn_act the activated product
+        self.ffn_act = torch.empty(tokens, ffn_act_dim, dtype=bf, device=device) if ffn_act_dim else None
         self.h = torch.empty(tokens, dim, dtype=bf, device=device)       # residual stream, both streams
         self.norm = torch.empty(tokens, dim, dtype=bf, device=device)
         self.qkv = torch.empty(tokens, 3 * dim, dtype=bf, device=device)
@@ -50,6 +52,7 @@ class StreamParams:
     out: str
     ff: str
     rope: Optional[torch.Tensor]
+    swiglu: bool = False      # Flux2FeedForward: linear_in -> silu(x1) * x2 -> linear_out instead of the gelu-tanh FeedForward
 
 
 def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: Sequence[StreamParams], heads: int,
@@ -85,8 +88,14 @@ def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: S
         ops.linear(ws.attn[s.rows], w[s.out + ".weight"], w.get(s.out + ".bias"), epilogue=ops.EPI_GATE_RES, out=h,
                    gate=gate_msa)
         ops.adaln_zero_modulate(h, scale_mlp, shift_mlp, eps=eps, out=ws.norm[s.rows])
-        ops.mlp_gelu_(h, ws.norm[s.rows], w[s.ff + ".net.0.proj.weight"], w.get(s.ff + ".net.0.proj.bias"),
-                      w[s.ff + ".net.2.weight"], w.get(s.ff + ".net.2.bias"), gate_mlp, ws.ffn)
+        if s.swiglu:
+            ops.linear(ws.norm[s.rows], w[s.ff + ".linear_in.weight"], w.get(s.ff + ".linear_in.bias"), out=ws.ffn[s.rows])
+            ops.swiglu(ws.ffn[s.rows], out=ws.ffn_act[s.rows])
+            ops.linear(ws.ffn_act[s.rows], w[s.ff + ".linear_out.weight"], w.get(s.ff + ".linear_out.bias"),
+                       epilogue=ops.EPI_GATE_RES, out=h, gate=gate_mlp)
+        else:
+            ops.mlp_gelu_(h, ws.norm[s.rows], w[s.ff + ".net.0.proj.weight"], w.get(s.ff + ".net.0.proj.bias"),
+                          w[s.ff + ".net.2.weight"], w.get(s.ff + ".net.2.bias"), gate_mlp, ws.ffn)
 
 
 def fuse_linears(w: Dict[str, torch.Tensor], dst: str, srcs: Sequence[str]) -> None:

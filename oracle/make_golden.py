@@ -364,9 +364,57 @@ def golden_hy15vae():
     print("hy15_vae", {k: v.shape for k, v in out.items()})
 
 
+FLUX2_CONFIGS = {
+    # name: (oracle make_weights kwargs, latent grid (h, w), text tokens)
+    "flux2_s56": (dict(dim=256, heads=2, num_layers=2, num_single_layers=2, in_channels=16, joint_dim=48, guidance_embeds=False), (6, 8), 8),
+    "flux2_s200": (dict(dim=256, heads=2, num_layers=1, num_single_layers=1, in_channels=16, joint_dim=48, guidance_embeds=True), (12, 16), 8),
+}
+
+
+def flux2_ids(gh, gw, n_txt):
+    """4-axis position ids as the Flux2 engine prepares them: image (t=0, h, w, l=0), text (0, 0, 0, l)."""
+    img = torch.zeros(gh * gw, 4)
+    img[:, 1] = torch.arange(gh * gw) // gw
+    img[:, 2] = torch.arange(gh * gw) % gw
+    txt = torch.zeros(n_txt, 4)
+    txt[:, 3] = torch.arange(n_txt)
+    return img, txt
+
+
+def golden_flux2():
+    """Reference Flux2Transformer2DModel (BASELINE configs[0] family) with the `sdpa` backend, fp32 and bf16."""
+    import flux2_dit
+
+    fm = bootstrap.ref("src.transformer.flux2.base.model")
+    a = bootstrap.ref("src.attention.functions")
+    a.attention_register.set_default("sdpa")
+    for name, (cfg, (gh, gw), n_txt) in FLUX2_CONFIGS.items():
+        w32 = flux2_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+        x = torch.randn(1, gh * gw, cfg["in_channels"], generator=torch.Generator().manual_seed(42))
+        enc = torch.randn(1, n_txt, cfg["joint_dim"], generator=torch.Generator().manual_seed(43))
+        t = torch.tensor([0.5])
+        g = torch.tensor([4.0]) if cfg["guidance_embeds"] else None
+        img_ids, txt_ids = flux2_ids(gh, gw, n_txt)
+        out = dict(hidden=f32(x), enc=f32(enc), timestep=t.numpy(), img_ids=img_ids.numpy(), txt_ids=txt_ids.numpy())
+        if g is not None:
+            out["guidance"] = g.numpy()
+        for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+            model = fm.Flux2Transformer2DModel(
+                in_channels=cfg["in_channels"], num_layers=cfg["num_layers"], num_single_layers=cfg["num_single_layers"],
+                attention_head_dim=cfg["dim"] // cfg["heads"], num_attention_heads=cfg["heads"],
+                joint_attention_dim=cfg["joint_dim"], guidance_embeds=cfg["guidance_embeds"]).eval()
+            model.load_state_dict(w32, strict=True)
+            model = model.to(dt)
+            with torch.inference_mode():
+                y = model(x.to(dt), enc.to(dt), t.to(dt), img_ids, txt_ids, None if g is None else g.to(dt), return_dict=False)[0]
+            out["out_" + tag] = f32(y)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15", "qwen", "hy15vae"]
+    which = sys.argv[1:] or ["dit", "attention", "scheduler", "vae", "flux", "hy15", "qwen", "hy15vae", "flux2"]
     for wname in which:
         fn = globals().get("golden_" + wname)
         if fn is None:

@@ -35,7 +35,7 @@ def setup():
 
     for name in ("transformer", "vae", "scheduler", "engine", "transformer.wan", "transformer.wan.base",
                  "vae.wan", "engine.wan", "transformer.flux", "transformer.flux.base", "transformer.hunyuanvideo15",
-                 "transformer.hunyuanvideo15.base", "transformer.qwenimage", "transformer.qwenimage.base", "vae.hunyuanvideo15"):
+                 "transformer.hunyuanvideo15.base", "transformer.qwenimage", "transformer.qwenimage.base", "vae.hunyuanvideo15", "transformer.flux2", "transformer.flux2.base"):
         full = "src." + name
         if full in sys.modules:
             continue

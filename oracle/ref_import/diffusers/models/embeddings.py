@@ -34,11 +34,11 @@ class Timesteps(nn.Module):
 
 
 class TimestepEmbedding(nn.Module):
-    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", out_dim=None, sample_proj_bias=True):
         super().__init__()
-        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim, sample_proj_bias)
         self.act = nn.SiLU()
-        self.linear_2 = nn.Linear(time_embed_dim, out_dim or time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, out_dim or time_embed_dim, sample_proj_bias)
 
     def forward(self, sample, condition=None):
         return self.linear_2(self.act(self.linear_1(sample)))

@@ -28,3 +28,7 @@ class BaseOutput(dict):
     def __init__(self, **kw):
         super().__init__(**kw)
         self.__dict__.update(kw)
+
+
+def is_torch_npu_available():
+    return False

@@ -232,3 +232,23 @@ def test_flux_denoise_loop_vs_oracle():
     ours, theirs = rel_l2(out, exact), rel_l2(ref, exact)
     assert ours <= max(1e-3, 1.5 * theirs), (ours, theirs)
     assert rel_l2(out, ref) <= 2e-2, rel_l2(out, ref)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """one whole Flux forward captured into a CUDA graph (apex_studio_b200.graph.GraphedCallable) and replayed
+    with new latents gives the eager result bit for bit."""
+    from apex_studio_b200.graph import GraphedCallable
+
+    name = "flux_s200"
+    cfg, g = CONFIGS[name], load(name)
+    m = _model(cfg, flux_dit.make_weights(**cfg, seed=1234, dtype=torch.float32))
+    x, enc, pooled, t, img_ids, txt_ids, guidance = inputs(g, torch.bfloat16)
+    x, enc, pooled, t = x.to(DEV), enc.to(DEV), pooled.to(DEV), t.to(DEV)
+    fwd = lambda xx, ee, pp, tt: m(xx, ee, pp, tt, img_ids, txt_ids, None, return_dict=False)[0]
+    graphed = GraphedCallable(fwd, (x, enc, pooled, t))
+    x2 = (x.float() * 0.5 + 0.1).bfloat16()
+    for xi in (x, x2, x):
+        eager = fwd(xi, enc, pooled, t).clone()
+        assert torch.equal(graphed(xi, enc, pooled, t), eager)
+    with pytest.raises(ValueError):
+        graphed(x[:, :10], enc, pooled, t)

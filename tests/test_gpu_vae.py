@@ -204,3 +204,31 @@ def test_frames_to_uint8_all_bf16_values():
     v = allv.view(3, 1, 1, -1).contiguous()
     got = frames_to_uint8(v.to(DEV))
     assert np.array_equal(got.cpu().numpy(), wan_vae.frames_to_uint8(v))
+
+
+def test_preview_renderer_on_a_side_stream_equals_synchronous_decode():
+    """Per-step preview decode (reference BaseEngine._render_step, base_engine.py:2927-2943): the frames delivered
+    by the side-stream renderer equal a synchronous decode + hand-off of the same latents, and the denoise stream keeps going."""
+    from apex_studio_b200 import denoise
+    from apex_studio_b200.vae import AutoencoderKLWan, WanVAEConfig
+    from apex_studio_b200.vae.wan import frames_to_uint8
+
+    gold = np.load(os.path.join(GOLDEN, "wan_vae.npz"))
+    vae = AutoencoderKLWan(WanVAEConfig(base_dim=32))
+    vae.load_state_dict(wan_vae.make_weights(base_dim=32, seed=7), device=DEV)
+    lat = torch.from_numpy(gold["untiled_latents"]).to(DEV)
+    fn = denoise.wan_preview_decode_fn(vae)
+    got = []
+    pr = denoise.PreviewRenderer(fn, got.append, interval=2)
+    total, lats = 5, []
+    for i in range(total):
+        cur = lat * (1.0 - 0.1 * i)
+        lats.append(cur)
+        pr.maybe_render(i, total, cur)
+        cur = None
+        torch.randn(512, 512, device=DEV) @ torch.randn(512, 512, device=DEV)        # "next step" work on the main stream
+    pr.finish()
+    assert pr.rendered_steps == [0, 1, 3] and len(got) == 3
+    for frames, step in zip(got, pr.rendered_steps):
+        ref = fn(lats[step]).cpu().numpy()
+        assert frames.dtype == np.uint8 and frames.shape == ref.shape and (frames == ref).all()

@@ -116,3 +116,38 @@ def test_expert_switch_is_integer_exact():
     assert got == expect
     assert sum(e == "high" for e, _ in got) == int((ts >= 875).sum())
     assert select_guidance_scale(torch.tensor(10), None, 5.0) == 5.0
+
+
+def test_preview_renderer_follows_the_reference_render_condition():
+    """render_on_step (engine/wan/shared/__init__.py:580-586): first step, every `interval`-th step, never the last one."""
+    import numpy as np
+
+    from apex_studio_b200 import denoise
+
+    got = []
+    pr = denoise.PreviewRenderer(lambda lat: (lat[0, :3, 0].permute(1, 2, 0).abs().clamp(0, 1) * 255).to(torch.uint8)[None],
+                                 lambda frames: got.append(frames), interval=3)
+    total = 10
+    for i in range(total):
+        pr.maybe_render(i, total, torch.full((1, 4, 2, 3, 5), float(i) / 10))
+    pr.finish()
+    assert pr.rendered_steps == [0, 2, 5, 8] and len(got) == 4
+    assert all(isinstance(f, np.ndarray) and f.dtype == np.uint8 and f.shape == (1, 3, 5, 3) for f in got)
+    assert got[1][0, 0, 0, 0] == int(0.2 * 255)
+    with pytest.raises(ValueError):
+        denoise.PreviewRenderer(lambda x: x, lambda f: None, interval=0)
+
+    class Sch:
+        def step(self, mo, t, x, return_dict=False):
+            return (x - 0.1 * mo.float(),)
+
+    fake = lambda hidden_states, timestep, return_dict=False, parallel=None, **kw: (hidden_states * 0.5,)
+    frames = []
+    out = denoise.moe_denoise(timesteps=torch.arange(5, 0, -1), latents=torch.ones(1, 4, 1, 2, 2), scheduler=Sch(),
+                              high_noise_transformer=fake, use_cfg_guidance=False, render_on_step=True,
+                              render_on_step_callback=frames.append, render_on_step_interval=2,
+                              preview_decode_fn=lambda lat: (lat[0, :3, 0].permute(1, 2, 0).clamp(0, 1) * 255).to(torch.uint8)[None])
+    assert len(frames) == 3 and out.shape == (1, 4, 1, 2, 2)          # steps 0, 1, 3 of 5 (never the last)
+    with pytest.raises(ValueError):
+        denoise.moe_denoise(timesteps=torch.arange(2), latents=torch.ones(1, 4, 1, 2, 2), scheduler=Sch(), high_noise_transformer=fake,
+                            use_cfg_guidance=False, render_on_step=True, render_on_step_callback=frames.append)
