@@ -117,3 +117,37 @@ def test_vae_production_width_tile_vs_exact_oracle():
     assert tuple(y.shape) == (1, 3, 5, 128, 128) and torch.isfinite(y).all()
     ours, theirs = rel_l2(y, exact), rel_l2(bf, exact)
     assert ours <= max(1e-3, 1.5 * theirs), (ours, theirs)
+
+
+@pytest.mark.parametrize("T,H,W,cin,cout", [(3, 8, 8, 32, 64), (2, 5, 7, 128, 48), (4, 16, 12, 64, 256)])
+def test_conv3d_on_prepadded_input_vs_torch_replicate_conv(T, H, W, cin, cout):
+    """HunyuanVideo15CausalConv3d (model.py:52-90) = replicate pad (2 frames in front, 1 pixel around) + valid 3x3x3 conv:
+    gather kernel + tcgen05 implicit GEMM on the pre-padded tensor; rel-L2 <= 4e-3 vs fp32 math of the same bf16 operands."""
+    from apex_studio_b200.vae.hunyuanvideo15 import conv3d_cl_padded, pad_norm_silu_cl
+    from apex_studio_b200.vae.wan import AutoencoderKLWan
+
+    torch.manual_seed(T * 100 + cin)
+    x = torch.randn(1, cin, T, H, W).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, 3) * (cin * 27) ** -0.5).bfloat16()
+    b = (torch.randn(cout) * 0.1).bfloat16()
+    res = torch.randn(1, cout, T, H, W).bfloat16()
+    ref = F.conv3d(F.pad(x.float(), (1, 1, 1, 1, 2, 0), mode="replicate"), w.float(), b.float())
+    xp = pad_norm_silu_cl(cl(x).to(DEV), None, False)
+    out = conv3d_cl_padded(xp, AutoencoderKLWan._tap_major(w.float()).to(DEV, torch.bfloat16), b.to(DEV), cout)
+    assert tuple(out.shape) == (T, H, W, cout) and rel_l2(cf(out), ref) <= 4e-3
+    out = conv3d_cl_padded(xp, AutoencoderKLWan._tap_major(w.float()).to(DEV, torch.bfloat16), b.to(DEV), cout, residual=cl(res).to(DEV))
+    assert rel_l2(cf(out), ref + res.float()) <= 4e-3
+
+
+def test_blend_without_clamp_matches_reference_order():
+    """AutoencoderKLHunyuanVideo15.tiled_decode (model.py:1060-1119): in-place blend_v then blend_h in bf16, crop, NO clamp."""
+    from apex_studio_b200.vae.hunyuanvideo15 import blend_tile_noclamp
+
+    torch.manual_seed(4)
+    up, left, tile = (torch.randn(1, 3, 2, 16, 16).bfloat16() * 2 for _ in range(3))
+    ref = hy15_vae._blend(left.clone(), hy15_vae._blend(up.clone(), tile.clone(), 4, 3), 4, 4)
+    frame = torch.zeros(3, 2, 12, 12, dtype=torch.bfloat16, device=DEV)
+    t = tile[0].to(DEV).contiguous()
+    blend_tile_noclamp(t, up[0].to(DEV).contiguous(), left[0].to(DEV).contiguous(), frame, 4, 12, 0, 0)
+    assert torch.equal(t.cpu(), ref[0]) and torch.equal(frame.cpu(), ref[0][..., :12, :12])
+    assert ref.abs().max() > 1.0                              # values beyond [-1, 1] survive: no clamp
