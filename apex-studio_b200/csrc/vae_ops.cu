@@ -22,6 +22,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // One pixel per SEG-lane segment of a warp (SEG = 16 or 32); lane i of the segment owns 16-byte chunks
 // i, i + SEG, ...  y = x / max(||x||_2, 1e-12) * sqrt(C) * gamma ; optional SiLU.  fp32 math, one rounding.
+// SiLU is evaluated as 0.5 v (1 + tanh(v / 2)) with tanh.approx: the exp + divide form costs two MUFU ops per element and
+// made these kernels SFU-bound at 38 % of the HBM bandwidth (profiles/r01_row_kernels_bw.json).
 template <int SEG, int ITERS>
 __global__ void __launch_bounds__(256)
 rmsnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -61,7 +63,7 @@ rmsnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = f[j] * inv * g[j];
-        if (silu) v = v / (1.0f + __expf(-v));
+        if (silu) v = 0.5f * v * (1.0f + fast_tanh(0.5f * v));  // silu = v * sigmoid(v), ONE MUFU op (tanh.approx) per element
         f[j] = v;
       }
       yr[c] = pack8(f);
@@ -228,7 +230,7 @@ pad_norm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v = f[j] * inv * g[j];
-          if (silu) v = v / (1.0f + __expf(-v));
+          if (silu) v = 0.5f * v * (1.0f + fast_tanh(0.5f * v));  // silu = v * sigmoid(v), ONE MUFU op (tanh.approx) per element
           f[j] = v;
         }
         yr[c] = pack8(f);
