@@ -12,6 +12,7 @@
 // diffusers FeedForward built at transformer/wan/base/model.py:1062 and called :1270, and the gate/residual
 // updates at model.py:1212-1213,1245-1251,1278-1279 (fused into the epilogue of the preceding projection).
 #include "host_util.cuh"
+#include <stdlib.h>
 #include "sm100_ptx.cuh"
 
 namespace b200 {
@@ -20,13 +21,23 @@ namespace linear {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int GROUP_M = 16;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr bool PAIR_BY_DEFAULT = true;    // validated on the B200: +10 % over the 1-CTA kernel (profiles/r01_gpu_session26_linear_pair.log)
+
+// NCTA = 1: one CTA per 128 x 256 output tile.  NCTA = 2 (cta_group::2): a CTA PAIR (cluster of 2 on one TPC) owns a
+// 256 x 256 tile -- each CTA stages its own 128 rows of A and only HALF of the W tile (128 of its 256 rows); the leader's
+// tcgen05.mma.cta_group::2 (M = 256) reads both halves, so every W byte is fetched from L2 and written to shared memory
+// once per 256 output rows instead of once per 128: 64 instead of 96 bytes per clock per SM, and 6 pipeline stages fit.
+template <int NCTA>
+struct Cfg {
+  static constexpr int B_ROWS = BN / NCTA;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct Params {
   int M, N, K;
@@ -57,8 +68,14 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
   tn = r / gsz;
 }
 
+template <int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  constexpr int STAGES = Cfg<NCTA>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES;
+  constexpr int B_ROWS = Cfg<NCTA>::B_ROWS;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair
+  const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -75,42 +92,60 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 1);         // pair: the LEADER's barrier collects the bytes of both CTAs (only the leader arrives)
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], 4 * NCTA);   // pair: the epilogue warps of BOTH CTAs release the leader's MMA issuer
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if constexpr (NCTA == 2) {
+      tmem_alloc_2sm(tmem_ptr, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_kb = (p.K + BK - 1) / BK;
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_tiles = p.tiles_m * p.tiles_n;      // tiles of (BM * NCTA) x BN
+  const int first_tile = blockIdx.x / NCTA;             // one tile stream per CTA pair
+  const int tile_step = gridDim.x / NCTA;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int tm, tn;
         tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * BK, tm * BM);
-          tma_load_2d(sb, &tmB, &full[stage], kb * BK, tn * BN);
+          if constexpr (NCTA == 2) {
+            // both CTAs fill their own shared memory; the bytes of both complete on the LEADER's barrier.  The peer never
+            // arrives: it may only refill a slot after the leader's MMAs of the previous round were committed (its own
+            // `empty` barrier, multicast), i.e. after the leader's barrier finished that round -- so its bytes can land
+            // before the leader's expect_tx of the same round (the tx-count goes negative transiently, which is legal).
+            const uint32_t lbar = mapa_u32(&full[stage], 0);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * BM);
+            tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN + static_cast<int>(cta_rank) * B_ROWS);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[stage], kb * BK, tm * BM);
+            tma_load_2d(sb, &tmB, &full[stage], kb * BK, tn * BN);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -119,13 +154,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, 0);
+    // ---------------------------------------------------------------- MMA issuer (pair: the leader CTA only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * NCTA, BN, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -140,29 +175,30 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if constexpr (NCTA == 2) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&acc_full[acc]);
+        if constexpr (NCTA == 2) umma_commit_2sm(&acc_full[acc]); else umma_commit(&acc_full[acc]);
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps (2..5)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int row = tm * BM + quad * 32 + lane;
+      const int row = (tm * NCTA + static_cast<int>(cta_rank)) * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -277,15 +313,18 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+        else mbar_arrive(&acc_empty[acc]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (NCTA == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -307,6 +346,15 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return B200_ERR_ALIGN;
   if (gate && (reinterpret_cast<uintptr_t>(gate) & 15)) return B200_ERR_ALIGN;
 
+  // CTA-pair (cta_group::2) kernel: B200_LINEAR_2CTA=1 forces it, =0 disables it; default: see use_pair below.
+  static int pair_mode = -2;
+  if (pair_mode == -2) {
+    const char* ev = getenv("B200_LINEAR_2CTA");
+    pair_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+  }
+  const bool use_pair = pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && M > BM);
+  const int ncta = use_pair ? 2 : 1;
+
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -318,7 +366,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[2] = {1, (uint64_t)ldw};
-    uint32_t box[2] = {BK, BN};
+    uint32_t box[2] = {BK, (uint32_t)(BN / ncta)};
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -330,18 +378,50 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.ldc = ldc;
   p.epi = epilogue;
   p.bias_row = bias_row;
-  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_m = (M + BM * ncta - 1) / (BM * ncta);
   p.tiles_n = (N + BN - 1) / BN;
   const int total = p.tiles_m * p.tiles_n;
-  const int grid = total < num_sms() ? total : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return B200_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_LAUNCH;
     attr_done = true;
   }
-  linear_kernel<<<grid, NUM_THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  if (use_pair) {
+    int pairs_avail = num_sms() / 2;
+    if (const char* ev = getenv("B200_LINEAR_PAIRS")) pairs_avail = atoi(ev) > 0 ? atoi(ev) : pairs_avail;   // experiments
+    const int pairs = total < pairs_avail ? total : pairs_avail;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static bool dbg_done = false;
+    if (!dbg_done && getenv("B200_LINEAR_DEBUG")) {
+      int ncl = -1;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, linear_kernel<2>, &cfg);
+      fprintf(stderr, "[apex_b200] linear pair kernel: max active clusters %d (err %d), launching %d pairs\n", ncl, (int)e, pairs);
+      dbg_done = true;
+    }
+    if (cudaLaunchKernelEx(&cfg, linear_kernel<2>, tmA, tmB, p) != cudaSuccess) {
+      cudaGetLastError();
+      return B200_ERR_LAUNCH;
+    }
+  } else {
+    const int grid = total < num_sms() ? total : num_sms();
+    linear_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB, p);
+  }
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
