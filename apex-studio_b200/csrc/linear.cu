@@ -1,10 +1,13 @@
 // b200_linear: C = epilogue(A @ W^T + bias) on the 5th-gen tensor cores.
 //
-// Persistent, warp-specialised kernel, one CTA per SM:
-//   warp 0      TMA producer   (A tile 128x64, W tile 256x64, 128B swizzle, 4-stage mbarrier ring)
-//   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128 N=256 K=16, fp32 accumulators in TMEM,
-//                               two accumulator buffers = all 512 TMEM columns, so the epilogue of tile i
-//                               overlaps the main loop of tile i+1)
+// Persistent, warp-specialised kernel, one CTA per SM; by default the CTAs work in PAIRS (cluster of 2, cta_group::2):
+//   warp 0      TMA producer   (A tile 128x64 + this CTA's 128 of the 256 W rows, 128B swizzle, 6-stage mbarrier ring;
+//                               both CTAs' loads complete on the LEADER's barrier)
+//   warp 1      MMA issuer     (leader CTA only: tcgen05.mma cta_group::2, M=256 N=256 K=16 -- 128 rows per CTA, the W
+//                               halves of both CTAs -- fp32 accumulators in the TMEM of both CTAs, two accumulator
+//                               buffers = all 512 TMEM columns, so the epilogue of tile i overlaps the main loop of tile
+//                               i+1; tcgen05.commit.multicast releases the smem slots / publishes the accumulator in both)
+//   (M <= 128, or B200_LINEAR_2CTA=0: the 1-CTA form -- 128x256 tile, W tile 256x64, 4 stages, cta_group::1)
 //   warps 2-5   epilogue       (tcgen05.ld 32x32b, bias / gelu-tanh / gate*acc+residual, 16-byte stores)
 // Tiles are walked in groups of GROUP_M row-tiles so that the W panel of a group stays in L2.
 //
