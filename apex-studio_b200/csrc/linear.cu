@@ -33,12 +33,15 @@ constexpr bool PAIR_BY_DEFAULT = true;    // validated on the B200: +10 % over t
 // 256 x 256 tile -- each CTA stages its own 128 rows of A and only HALF of the W tile (128 of its 256 rows); the leader's
 // tcgen05.mma.cta_group::2 (M = 256) reads both halves, so every W byte is fetched from L2 and written to shared memory
 // once per 256 output rows instead of once per 128: 64 instead of 96 bytes per clock per SM, and 6 pipeline stages fit.
-template <int NCTA>
+// BN_T: N extent of the output tile.  256 everywhere except the SMALL-M form <1, 64>: the 512-row text streams of the
+// dual-stream image models give only 24-96 tiles of 256 columns on 148 SMs; 64-column tiles quadruple the tile count
+// (profiles/r01_gemm_shapes_vs_cublas_pair.txt: 236-755 TFLOP/s on those shapes with 256-column tiles).
+template <int NCTA, int BN_T = BN>
 struct Cfg {
-  static constexpr int B_ROWS = BN / NCTA;
+  static constexpr int B_ROWS = BN_T / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+  static constexpr int STAGES = NCTA == 2 ? 6 : (BN_T == 64 ? 8 : 4);   // 64-column tiles: 128 MMA cycles per k-block, deeper ring
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -51,6 +54,7 @@ struct Params {
   int epi;
   int bias_row;
   int tiles_m, tiles_n;
+  int group_m;   // row-tiles per rasterisation group (the W panel of a group stays in L2)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -61,22 +65,22 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + fast_tanh(inner));
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-  const int per_group = GROUP_M * tiles_n;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  const int per_group = group_m * tiles_n;
   const int group = tile / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsz = min(tiles_m - first_m, GROUP_M);
+  const int first_m = group * group_m;
+  const int gsz = min(tiles_m - first_m, group_m);
   const int r = tile - group * per_group;
   tm = first_m + r % gsz;
   tn = r / gsz;
 }
 
-template <int NCTA>
+template <int NCTA, int BN_T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
-  constexpr int STAGES = Cfg<NCTA>::STAGES;
-  constexpr int STAGE_BYTES = Cfg<NCTA>::STAGE_BYTES;
-  constexpr int B_ROWS = Cfg<NCTA>::B_ROWS;
+  constexpr int STAGES = Cfg<NCTA, BN_T>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<NCTA, BN_T>::STAGE_BYTES;
+  constexpr int B_ROWS = Cfg<NCTA, BN_T>::B_ROWS;
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
@@ -130,7 +134,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int tm, tn;
-        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -143,11 +147,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint32_t lbar = mapa_u32(&full[stage], 0);
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
             tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * BM);
-            tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN + static_cast<int>(cta_rank) * B_ROWS);
+            tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN_T + static_cast<int>(cta_rank) * B_ROWS);
           } else {
             mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
             tma_load_2d(sa, &tmA, &full[stage], kb * BK, tm * BM);
-            tma_load_2d(sb, &tmB, &full[stage], kb * BK, tn * BN);
+            tma_load_2d(sb, &tmB, &full[stage], kb * BK, tn * BN_T);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -159,7 +163,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (pair: the leader CTA only)
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * NCTA, BN, 0);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * NCTA, BN_T, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -196,7 +200,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     int it = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       int tm, tn;
-      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
@@ -205,8 +209,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const bool row_ok = row < p.M;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = tn * BN + c * 32;
+      for (int c = 0; c < BN_T / 32; ++c) {
+        const int col0 = tn * BN_T + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_x32(t_addr + c * 32, r);
@@ -355,8 +359,21 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     const char* ev = getenv("B200_LINEAR_2CTA");
     pair_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
   }
-  const bool use_pair = pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && M > BM);
+  bool use_pair = pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && M > BM);
+  // small-M form: fewer than one wave of 128 x 256 tiles -> 128 x 64 tiles on single CTAs.  OFF by default (B200_LINEAR_SMALLM=1
+  // enables): measured on the FLUX text-stream shapes it wins only 3-5 us where there are <= 48 tiles (512x3072x3072: 25.6 -> 20.6 us)
+  // and loses where there are 144 (512x9216x3072: 27.2 -> 35.9 us) -- N = 64 MMAs and 4x the A re-reads eat the extra parallelism
+  // (profiles/r01_gpu_session29_smallm.log).  Split-K is the better tool for these shapes.
+  static int smallm_mode = -2;
+  if (smallm_mode == -2) {
+    const char* ev = getenv("B200_LINEAR_SMALLM");
+    smallm_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+  }
+  const int tiles256 = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const bool small_m = smallm_mode == 1 && pair_mode != 1 && M <= 512 && M > 16 && tiles256 < num_sms() && N >= 256;
+  if (small_m) use_pair = false;
   const int ncta = use_pair ? 2 : 1;
+  const int bn = small_m ? 64 : BN;
 
   CUtensorMap tmA, tmB;
   {
@@ -369,7 +386,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[2] = {1, (uint64_t)ldw};
-    uint32_t box[2] = {BK, (uint32_t)(BN / ncta)};
+    uint32_t box[2] = {BK, (uint32_t)(bn / ncta)};
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -382,15 +399,19 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.epi = epilogue;
   p.bias_row = bias_row;
   p.tiles_m = (M + BM * ncta - 1) / (BM * ncta);
-  p.tiles_n = (N + BN - 1) / BN;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.group_m = GROUP_M;
+  if (const char* ev = getenv("B200_LINEAR_GROUP_M")) p.group_m = atoi(ev) > 0 ? atoi(ev) : GROUP_M;   // experiments
   const int total = p.tiles_m * p.tiles_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(linear_kernel<1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) != cudaSuccess)
       return B200_ERR_LAUNCH;
-    if (cudaFuncSetAttribute(linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(linear_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1, 64>::SMEM_BYTES) != cudaSuccess)
+      return B200_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) != cudaSuccess)
       return B200_ERR_LAUNCH;
     attr_done = true;
   }
@@ -413,17 +434,18 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     static bool dbg_done = false;
     if (!dbg_done && getenv("B200_LINEAR_DEBUG")) {
       int ncl = -1;
-      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, linear_kernel<2>, &cfg);
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, linear_kernel<2, BN>, &cfg);
       fprintf(stderr, "[apex_b200] linear pair kernel: max active clusters %d (err %d), launching %d pairs\n", ncl, (int)e, pairs);
       dbg_done = true;
     }
-    if (cudaLaunchKernelEx(&cfg, linear_kernel<2>, tmA, tmB, p) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, linear_kernel<2, BN>, tmA, tmB, p) != cudaSuccess) {
       cudaGetLastError();
       return B200_ERR_LAUNCH;
     }
   } else {
     const int grid = total < num_sms() ? total : num_sms();
-    linear_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB, p);
+    if (small_m) linear_kernel<1, 64><<<grid, NUM_THREADS, Cfg<1, 64>::SMEM_BYTES, st>>>(tmA, tmB, p);
+    else linear_kernel<1, BN><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB, p);
   }
   B200_CHECK_LAUNCH();
   return B200_OK;
