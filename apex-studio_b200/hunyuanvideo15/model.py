@@ -182,10 +182,7 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
         self.device = dev
         g = torch.Generator(device=dev).manual_seed(seed)
         c, bf = self.config, torch.bfloat16
-        shapes = {}
         d = c.inner_dim
-        for k in self.state_dict_keys():
-            shapes[k] = None
         w: Dict[str, torch.Tensor] = {}
 
         def rnd(*shape, scale=std, base=0.0):
