@@ -29,7 +29,8 @@ constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two [128 x 64] swizzled hal
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr int KV_SLOTS = 4;
 constexpr int NUM_THREADS = 384;  // warpgroups: softmax0 | softmax1 | {TMA, MMA, 2 idle warps}
-constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256;
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4;  // VARIANT 7: per (tile, column half, row) float exchanged between the two warps of a row
+constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256 + XCH_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 // setmaxnreg budget.  The CTA owns 168 regs x 384 threads = 504 per (softmax0, softmax1, other) warp triple; the
 // increase BLOCKS until the pool has enough registers, so 2 * REGS_SOFTMAX + REGS_OTHER must not exceed 504
@@ -142,7 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&p_full[t], VARIANT == 7 ? 8 : 4);
       mbar_init(&p_half[t], 4);
       mbar_init(&o_done[t], 1);
     }
@@ -277,6 +278,137 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ softmax warps
     setmaxnreg_inc<REGS_SOFTMAX>();
+    if constexpr (VARIANT == 7) {
+      // VARIANT 7 -- "split-row" softmax.  In variants 1-6 ONE warp owns all 128 key columns of its 32 query rows, so a
+      // tile-step of softmax costs that warp >= 96 MUFU.EX2 instructions x 8 issue cycles = 768 cycles on its SMSP plus
+      // TMEM / barrier latencies (~1400 in total) while the tensor pipe needs only 1024 cycles for the other tile's
+      // PV + S: the pipe idles 28 % of the time (ncu: 72 % active).  Here BOTH warpgroups work on EVERY tile: warp q of
+      // warpgroup 0 takes key columns 0..63 and warp q of warpgroup 1 columns 64..127 of the same 32 rows, tiles are
+      // processed alternately (t = 0, 1, 0, 1, ...), the row maximum is combined through shared memory (one named
+      // barrier of the two warps), the row sum stays split until the epilogue.  Per-tile softmax latency halves.
+      const int half = warp >> 2;   // key-column half of every S tile this warp owns
+      const int quad = warp & 3;    // TMEM lane quadrant (a warp may touch lanes 32 * (warp % 4) .. + 32)
+      const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+      float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [tile][half][128 rows]
+      const int rowi = quad * 32 + lane;
+      const float sl2 = p.scale_log2;
+      float m[2] = {-INFINITY, -INFINITY};
+      float l[2] = {0.f, 0.f};
+      for (int j = 0; j < n_kv; ++j) {
+        const int valid = p.Sk - j * BKV;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t s_addr = tmem_base + lane_base + t * 128;
+          const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
+          mbar_wait(&s_full[t], j & 1);
+          tc_fence_after();
+          uint32_t s[64];
+          tmem_ld_x32(s_addr + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_ld_x32(s_addr + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          tmem_ld_wait();
+          if (valid < BKV) {
+#pragma unroll
+            for (int k = 0; k < 64; ++k)
+              if (half * 64 + k >= valid) s[k] = 0xff800000u;  // -inf
+          }
+          float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+#pragma unroll
+          for (int k = 2; k < 62; k += 4) {
+            mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+          }
+          mx0 = fmax3(mx0, __uint_as_float(s[62]), __uint_as_float(s[63]));
+          const float mx_half = fmaxf(mx0, mx1);
+          // combine with the other half of the row.  The barrier also orders this warp's S loads before the partner's P
+          // stores (P of columns 64..127 lands on the fp32 columns 32..63 that hold the S values of columns 32..63).
+          xch[(t * 2 + half) * 128 + rowi] = mx_half;
+          named_bar_sync(1 + quad, 64);
+          const float mx = fmaxf(mx_half, xch[(t * 2 + (half ^ 1)) * 128 + rowi]);
+          const float m_new = fmaxf(m[t], mx * sl2);
+          if (j == 0) {
+            m[t] = m_new;
+          } else if (__any_sync(0xffffffffu, (m_new - m[t]) > RESCALE_THRESHOLD)) {
+            // same rows, same m_new in both warps of the pair -> same decision; each rescales its 64 columns of O_t
+            const float alpha = fast_exp2(m[t] - m_new);
+            l[t] *= alpha;
+            m[t] = m_new;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld_x32(o_addr + (half * 2 + c) * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+              tmem_st_x32(o_addr + (half * 2 + c) * 32, r);
+            }
+            tmem_st_wait();
+          }
+          const float2 sl2_2 = make_float2(sl2, sl2);
+          const float2 negm_2 = make_float2(-m[t], -m[t]);
+          float2 sum2 = make_float2(0.f, 0.f);
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int col = c * 32 + 2 * k;
+              const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
+              float2 e;
+              if (k < POLY_PAIRS) {
+                e = exp2_poly2(x);
+              } else {
+                e.x = fast_exp2(x.x);
+                e.y = fast_exp2(x.y);
+              }
+              sum2 = fadd2(sum2, e);
+              pk[c * 16 + k] = pack_bf16x2(e.x, e.y);
+            }
+          }
+          // bf16 P of key columns [64 * half, +64) = 32-bit columns [32 * half, +32) of the S region
+          tmem_st_x32(s_addr + half * 32, pk);
+          l[t] += sum2.x + sum2.y;
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+        }
+      }
+      // epilogue: O / (l_half0 + l_half1) -> bf16 -> global; each warp stores its 64 of the 128 head channels
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
+        mbar_wait(&o_done[t], (n_kv - 1) & 1);
+        tc_fence_after();
+        xch[(t * 2 + half) * 128 + rowi] = l[t];
+        named_bar_sync(1 + quad, 64);
+        const float inv_l = 1.0f / (l[t] + xch[(t * 2 + (half ^ 1)) * 128 + rowi]);
+        const int row = q_block * (2 * BQ) + t * BQ + rowi;
+        __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
+        if (p.n_peers > 0 && row < p.Sq) {
+          const int d = row / p.rows_per_rank;
+          orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
+                 static_cast<int64_t>(head + p.head_off) * p.o_sh;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
+          uint32_t r[32];
+          tmem_ld_x32(o_addr + c * 32, r);
+          tmem_ld_wait();
+          if (row < p.Sq) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
+              o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
+              o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
+              o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
+              reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
+            }
+          }
+        }
+      }
+    } else {
     const int t = warp >> 2;     // query tile
     const int quad = warp & 3;   // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -467,6 +599,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+    }  // variants 1-6
   }
 
   tc_fence_before();
@@ -520,13 +653,14 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   // B200_ATTN_VARIANT selects the kernel variant for A/B measurements (default DEFAULT_VARIANT):
   //   1 two-pass bring-up softmax | 2 single pass + f32x2 + 25 % polynomial exp2 | 3 = 2 + split P hand-off
   //   4 = 2 + FMNMX3 row max | 5 = 4 with 12.5 % polynomial | 6 = 4 with 37.5 %
+  //   7 = split-row softmax: both warpgroups share every tile (64 key columns each), halving the per-tile softmax latency
   // Measured on B200 (profiles/r01_gpu_session7_attn_ab.log): at 40 heads x 75600^2 every variant >= 2 lands within
   // 1 % (1213-1228 TFLOP/s) because the run is power-capped (~1.5 GHz); a double-buffered-S design with 64-key steps
   // was also tried and was no faster, so it was dropped.
   static int variant = 0;
   if (variant == 0) {
     const char* ev = getenv("B200_ATTN_VARIANT");
-    variant = (ev && ev[0] >= '1' && ev[0] <= '6') ? (ev[0] - '0') : DEFAULT_VARIANT;
+    variant = (ev && ev[0] >= '1' && ev[0] <= '7') ? (ev[0] - '0') : DEFAULT_VARIANT;
     bool ok = true;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
@@ -534,6 +668,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
     if (!ok) {
       variant = 0;
       return B200_ERR_LAUNCH;
@@ -578,7 +713,8 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     case 3: attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 4: attn_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
     case 5: attn_fwd_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    default: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    case 6: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+    default: attn_fwd_kernel<7><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
   }
   B200_CHECK_LAUNCH();
   return B200_OK;

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""A/B of one attention kernel variant (B200_ATTN_VARIANT is read once per process): correctness on small / ragged / cross shapes vs
+fp32 math, then the Wan self-attention launch (40 heads x 75600^2) timed with CUDA events."""
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from apex_studio_b200 import ops  # noqa: E402
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+def main():
+    res = {"variant": os.environ.get("B200_ATTN_VARIANT", "default")}
+    for (B, H, Sq, Sk) in [(1, 2, 300, 333), (2, 3, 1000, 777), (1, 32, 1024, 1024), (1, 4, 2048, 512), (1, 2, 128, 64), (1, 1, 4000, 4100)]:
+        torch.manual_seed(42)
+        q, k, v = (torch.randn(B, H, s, 128, device="cuda", dtype=torch.bfloat16) for s in (Sq, Sk, Sk))
+        out = ops.attention(q, k, v)
+        ref = torch.softmax((q.float() @ k.float().transpose(-1, -2)) / math.sqrt(128), dim=-1) @ v.float()
+        res[f"rel_{B}x{H}x{Sq}x{Sk}"] = round(rel(out, ref), 5)
+        res["nan"] = res.get("nan", False) or bool(torch.isnan(out.float()).any())
+    if len(sys.argv) > 1 and sys.argv[1] == "bench":
+        q, k, v = (torch.randn(1, 40, 75600, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+        out = ops.attention(q, k, v)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(q[:, :2], k[:, :2], v[:, :2])
+        res["rel_full_2heads_vs_sdpa"] = round(rel(out[:, :2], ref), 5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.attention(q, k, v, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        res["ms_40x75600"] = round(ms, 2)
+        res["tflops"] = round(4.0 * 40 * 75600 * 75600 * 128 / ms / 1e9, 1)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
