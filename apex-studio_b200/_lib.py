@@ -19,6 +19,7 @@ SIGNATURES = {
     "b200_version": (_i, []),
     "b200_strerror": (ctypes.c_char_p, [_i]),
     "b200_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p]),
+    "b200_attn_fwd_prof": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p, _i, _p]),
     "b200_linear": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "b200_layernorm_modulate": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i64, _i64, _f, _p]),
     "b200_rmsnorm_rope": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p]),

@@ -3,14 +3,30 @@
 // One CTA owns TWO 128-row query tiles of one (batch, head) and streams all key/value tiles past them:
 //   warps 0-3   softmax for query tile 0 (one query row per thread, row == TMEM lane)
 //   warps 4-7   softmax for query tile 1
-//   warp  8     TMA producer: Q once, then K_j, V_j through a ring of 32 KB slots (128B-swizzled tiles)
+//   warp  8     TMA producer: Q once, then K_j, V_j through a ring of shared-memory slots (128B-swizzled tiles)
 //   warp  9     MMA issuer:   S_t = Q_t K_j^T  (tcgen05.mma, A and B from shared memory, fp32 S in TMEM)
 //                             O_t += P_t V_j   (A = bf16 P read straight from TMEM, B = V MN-major in smem)
-// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_t overwrites the first 64 columns of S_t.
-// The issue order  PV0(j) S0(j+1) PV1(j) S1(j+1)  lets the tensor pipe work on one query tile while the
-// other tile's softmax runs, and makes "S_t(j+1) ready" imply "PV_t(j) finished", so the softmax warps
-// can rescale O_t in place (lazily, only when the running max grows by more than 2^8) without a
-// separate correction stage.
+//
+// PIPE = 1 (default, round 2) -- the DECOUPLED pipeline.  TMEM (512 columns): S | P0 | P1 | O0 | O1 = 128 + 64 + 64 +
+//   128 + 128.  ONE S buffer is shared by both query tiles: a softmax warp pulls its whole 128-column S row into
+//   registers in ~50 cycles and hands the buffer back ("S free"), so the tensor pipe computes S_t(j+1) WHILE softmax_t(j)
+//   is still working in registers, and P_t has its own columns.  Issue order  S1(j+1) PV0(j) S0(j+2) PV1(j).  The round-1
+//   layout (S0 | S1 | O0 | O1, P_t aliasing S_t) forced S_t(j+1) behind PV_t(j), which put the whole chain
+//   PV_t(j) -> S_t(j+1) -> softmax_t(j+1) -> "P ready" in series: 512 + 512 + ~1700 + ~290 = 3036 cycles per key tile against
+//   2048 cycles of tensor work (measured with b200_attn_fwd_prof: period 3084, profiles/r02_attn_timeline_*.log).  Decoupled,
+//   the period is max(2048, softmax + ~440).  Hazards: (1) P_t(j+1) may only be stored after PV_t(j) has read P_t(j) ->
+//   the softmax warps wait for "O done"(j) right before their P stores (it has long completed in steady state);
+//   (2) the lazy rescale of O_t (only when the running max grows by more than 2^8) waits for the same barrier.
+// PIPE = 0 -- the round-1 kernel (1-CTA only), kept as the A/B partner (B200_ATTN_PIPE=0).
+//
+// NCTA = 2: the CTAs work in PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2).  A pair owns 512 query rows; every
+// MMA is M = 256 (128 rows in each CTA's TMEM).  The B operands are SPLIT across the pair: each CTA stages only 64 of the
+// 128 keys of K_j (S = Q K^T: N = 128 keys, N/2 per CTA) and only 64 of the 128 channels of V_j (O += P V: N = 128
+// channels, N/2 per CTA), so every K/V byte is fetched from L2 and written to shared memory once per 512 query rows
+// instead of once per 256, and the operand reads of the tensor pipe drop from 192 KB to 128 KB per key tile per SM.  Both
+// CTAs' TMA bytes complete on the LEADER's mbarrier; the leader's single MMA thread issues for both;
+// tcgen05.commit.multicast publishes "S ready", "O done" and "slot free" in both CTAs; the peer's softmax warps signal
+// "S free" / "P ready" on the leader's barriers through remote (shared::cluster) arrives.
 //
 // Replaces attention_register.call(q, k, v) -- attention/functions.py:84 (`sdpa` :338-377 is the gold
 // backend) as called by transformer/wan/base/attention.py:397.
@@ -23,22 +39,28 @@ namespace b200 {
 namespace attn {
 
 constexpr int D = 128;
-constexpr int BQ = 128;   // rows per query tile
+constexpr int BQ = 128;   // rows per query tile (per CTA)
 constexpr int BKV = 128;  // keys per tile
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two [128 x 64] swizzled half tiles
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr int KV_SLOTS = 4;
 constexpr int NUM_THREADS = 384;  // warpgroups: softmax0 | softmax1 | {TMA, MMA, 2 idle warps}
-constexpr int XCH_BYTES = 2 * 2 * 128 * 4;  // VARIANT 7: per (tile, column half, row) float exchanged between the two warps of a row
-constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * TILE_BYTES + 1024 + 256 + XCH_BYTES;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 // setmaxnreg budget.  The CTA owns 168 regs x 384 threads = 504 per (softmax0, softmax1, other) warp triple; the
 // increase BLOCKS until the pool has enough registers, so 2 * REGS_SOFTMAX + REGS_OTHER must not exceed 504
 // (216/80 = 512 deadlocked every CTA in bring-up).
 constexpr int REGS_SOFTMAX = 208;
 constexpr int REGS_OTHER = 88;
-constexpr int DEFAULT_VARIANT = 2;
+constexpr bool PAIR_BY_DEFAULT = false;   // CTA pairs: set once measured faster than single CTAs on the B200
 static_assert(2 * REGS_SOFTMAX + REGS_OTHER <= 504, "setmaxnreg.inc would wait forever");
+
+template <int NCTA>
+struct Cfg {
+  static constexpr int KV_BYTES = TILE_BYTES / NCTA;   // bytes of one K (or V) tile staged by ONE CTA
+  // ring depth: the decoupled pipeline issues S_t(j+2) while V_j is still in use, so K_{j+2} must land about one key tile
+  // ahead -- 5 slots of 32 KB (4 stalled the MMA issuer ~800 cycles per key tile on the K wait: profiles/r02_attn_timeline_*.log)
+  static constexpr int KV_SLOTS = NCTA == 2 ? 8 : 5;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * KV_BYTES + 1024 + 256;
+};
 
 struct Params {
   int B, H, Sq, Sk;
@@ -51,15 +73,16 @@ struct Params {
   int n_peers;        // 0 = plain store into `o`
   int rows_per_rank;  // S / P
   int head_off;       // first global head computed by this rank
+  int exp_flags;      // experiments (B200_ATTN_EXP): bit 0 = issue every S tile as two N = 64 MMA groups
+  long long* prof;    // PROF kernels only: [steps][16] SM-clock timestamps of CTA (0,0,0) (b200_attn_fwd_prof)
+  int prof_steps;
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// Softmax of one 128-key tile for one query row (thread == row == TMEM lane).
-// VARIANT 1 (bring-up): two passes over TMEM in 32-column chunks (max, then exp), scalar fp32 math.
-// VARIANT 2 (default):  one pass -- the whole S row is loaded into registers with four back-to-back tcgen05.ld,
-//   packed fma/add (.f32x2) for the scale-and-subtract and the row sum, and POLY_PAIRS of every 16 column
-//   pairs take a Cody-Waite + cubic-polynomial exp2 on the FMA pipe instead of MUFU.EX2 (the SFU is the
-//   co-bottleneck: 128x128 exps at 16/clk/SM take as long as the two 128x128x128 MMAs of the tile).
+// Softmax of one 128-key tile for one query row (thread == row == TMEM lane): one pass -- the whole S row is loaded
+// into registers with four back-to-back tcgen05.ld, packed fma/add (.f32x2) for the scale-and-subtract and the row
+// sum, and POLY_PAIRS of every 16 column pairs take a Cody-Waite + cubic-polynomial exp2 on the FMA pipe instead of
+// MUFU.EX2 (the SFU is the co-bottleneck: 128x128 exps at 16/clk/SM take as long as the two 128x128x128 MMAs of the tile).
 // ---------------------------------------------------------------------------------------------------------
 B200_DEVICE float2 ffma2(float2 a, float2 b, float2 c) {
   uint64_t ra, rb, rc, rd;
@@ -99,38 +122,54 @@ B200_DEVICE float2 exp2_poly2(float2 x) {
   return r;
 }
 
-constexpr int POLY_PAIRS = 4;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
-
 B200_DEVICE float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
 
-template <int VARIANT>
+constexpr int POLY_PAIRS = 4;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
+
+#define ATTN_STAMP(step, k)                                                                     \
+  do {                                                                                         \
+    if (PROF && prof_cta && (step) < p.prof_steps) p.prof[(step) * 16 + (k)] = clock64();       \
+  } while (0)
+
+template <int NCTA, int PIPE, bool PROF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, Params p) {
+  constexpr int KV_SLOTS = Cfg<NCTA>::KV_SLOTS;
+  constexpr int KV_BYTES = Cfg<NCTA>::KV_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                      // 2 tiles
-  uint8_t* kv_smem = smem + 2 * TILE_BYTES;    // KV_SLOTS tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KV_SLOTS * TILE_BYTES);
-  uint64_t* q_full = bars;                 // [1]
-  uint64_t* kv_full = bars + 1;            // [KV_SLOTS]
-  uint64_t* kv_empty = kv_full + KV_SLOTS; // [KV_SLOTS]
-  uint64_t* s_full = kv_empty + KV_SLOTS;  // [2]
-  uint64_t* p_full = s_full + 2;           // [2]
-  uint64_t* o_done = p_full + 2;           // [2]
-  uint64_t* p_half = o_done + 2;           // [2]  VARIANT 3: second half of P (keys 64..127) written
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_half + 2);
+  uint8_t* kv_smem = smem + 2 * TILE_BYTES;    // KV_SLOTS slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KV_SLOTS * KV_BYTES);
+  uint64_t* q_full = bars;                 // [1]          (pair: the leader's collects both CTAs' bytes)
+  uint64_t* kv_full = bars + 1;            // [KV_SLOTS]   (pair: leader's)
+  uint64_t* kv_empty = kv_full + KV_SLOTS; // [KV_SLOTS]   (pair: multicast commit -> both CTAs)
+  uint64_t* s_full = kv_empty + KV_SLOTS;  // [2]          (multicast)
+  uint64_t* p_full = s_full + 2;           // [2]          (pair: leader's, 4 local + 4 remote warps arrive)
+  uint64_t* o_done = p_full + 2;           // [2]          (multicast)
+  uint64_t* s_free = o_done + 2;           // [1]  PIPE 1: the shared S buffer has been pulled into registers (pair: leader's)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + 1);
+  // TMEM columns
+  constexpr uint32_t S_COL0 = 0, S_COL1 = PIPE ? 0 : 128;                  // PIPE 1: one S buffer for both tiles
+  constexpr uint32_t P_COL0 = PIPE ? 128 : 0, P_COL1 = PIPE ? 192 : 128;   // PIPE 0: P_t aliases S_t
+  constexpr uint32_t O_COL0 = 256, O_COL1 = 384;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_block = blockIdx.x;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_kv = (p.Sk + BKV - 1) / BKV;
+  const bool prof_cta = PROF && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  // first query row of tile t of this CTA: a pair owns 2 * 256 rows, MMA tile t = rows [t * 256, +256) of them
+  const int row_base = static_cast<int>(blockIdx.x / NCTA) * (2 * BQ * NCTA) + static_cast<int>(cta_rank) * BQ;
+  constexpr int TILE_ROW_STEP = BQ * NCTA;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -143,134 +182,251 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], VARIANT == 7 ? 8 : 4);
-      mbar_init(&p_half[t], 4);
+      mbar_init(&p_full[t], 4 * NCTA);
       mbar_init(&o_done[t], 1);
     }
+    mbar_init(s_free, 4 * NCTA);
     fence_mbar_init();
   }
   if (warp == 9) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
+    if constexpr (NCTA == 2) {
+      tmem_alloc_2sm(tmem_ptr, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // Register budget per SMSP slot is 512 / 3 warps: give the two softmax warpgroups 224 registers each (a whole
-  // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 56.
+  // Register budget per SMSP slot is 512 / 3 warps: give the two softmax warpgroups 208 registers each (a whole
+  // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 88.
   // (one setmaxnreg per warpgroup, executed by all four of its warps at the same instruction, at the top of the
   // warpgroup's branch so that ptxas budgets the branch accordingly.)
   if (warp >= 8) {
    setmaxnreg_dec<REGS_OTHER>();
    if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (every CTA stages its own part)
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-      for (int t = 0; t < 2; ++t) {
-        const int row0 = q_block * (2 * BQ) + t * BQ;
-        tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
-        tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
-      }
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        for (int kv = 0; kv < 2; ++kv) {
+      if constexpr (NCTA == 2) {
+        // Both CTAs' bytes complete on the LEADER's barriers; only the leader arrives (expect_tx of both CTAs' bytes).
+        // The peer may only refill a slot after the leader's MMAs of the previous round were committed (its own
+        // kv_empty, multicast), i.e. after the leader's barrier finished that round, so its bytes can land before the
+        // leader's expect_tx of the same round (the tx-count goes negative transiently, which is legal).
+        const uint32_t qbar = mapa_u32(q_full, 0);
+        if (leader) mbar_arrive_expect_tx(q_full, 2 * 2 * TILE_BYTES);
+        for (int t = 0; t < 2; ++t) {
+          const int row0 = row_base + t * TILE_ROW_STEP;
+          tma_load_4d_2sm(q_smem + t * TILE_BYTES, &tmQ, qbar, 0, row0, head, batch);
+          tma_load_4d_2sm(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, qbar, 64, row0, head, batch);
+        }
+        int slot = 0;
+        uint32_t phase = 0;
+        const int r64 = static_cast<int>(cta_rank) * 64;
+        auto load_k = [&](int j) {   // K_j: this CTA's 64 keys x 128 channels = two [64 x 64] swizzled sub-tiles
           mbar_wait(&kv_empty[slot], phase ^ 1);
-          uint8_t* dst = kv_smem + slot * TILE_BYTES;
-          const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+          uint8_t* dst = kv_smem + slot * KV_BYTES;
+          const uint32_t fbar = mapa_u32(&kv_full[slot], 0);
+          if (leader) mbar_arrive_expect_tx(&kv_full[slot], 2 * KV_BYTES);
+          tma_load_4d_2sm(dst, &tmK, fbar, 0, j * BKV + r64, head, batch);
+          tma_load_4d_2sm(dst + KV_BYTES / 2, &tmK, fbar, 64, j * BKV + r64, head, batch);
+          if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
+        };
+        auto load_v = [&](int j) {   // V_j: all 128 keys x this CTA's 64 channels = one [128 x 64] swizzled half tile
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          uint8_t* dst = kv_smem + slot * KV_BYTES;
+          const uint32_t fbar = mapa_u32(&kv_full[slot], 0);
+          if (leader) mbar_arrive_expect_tx(&kv_full[slot], 2 * KV_BYTES);
+          tma_load_4d_2sm(dst, &tmV, fbar, r64, j * BKV, head, batch);
+          if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
+        };
+        load_k(0);
+        if (n_kv > 1) load_k(1);
+        for (int j = 0; j < n_kv; ++j) {
+          load_v(j);
+          if (j + 2 < n_kv) load_k(j + 2);
+        }
+      } else {
+        mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+        for (int t = 0; t < 2; ++t) {
+          const int row0 = row_base + t * TILE_ROW_STEP;
+          tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
+          tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
+        }
+        int slot = 0;
+        uint32_t phase = 0;
+        auto load_tile = [&](const CUtensorMap* tm, int j) {
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          uint8_t* dst = kv_smem + slot * KV_BYTES;
           mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
           tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV, head, batch);
           tma_load_4d(dst + HALF_BYTES, tm, &kv_full[slot], 64, j * BKV, head, batch);
-          if (++slot == KV_SLOTS) {
-            slot = 0;
-            phase ^= 1;
+          if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
+        };
+        if constexpr (PIPE == 1) {
+          load_tile(&tmK, 0);
+          if (n_kv > 1) load_tile(&tmK, 1);
+          for (int j = 0; j < n_kv; ++j) {
+            load_tile(&tmV, j);
+            if (j + 2 < n_kv) load_tile(&tmK, j + 2);
+          }
+        } else {
+          for (int j = 0; j < n_kv; ++j) {
+            load_tile(&tmK, j);
+            load_tile(&tmV, j);
           }
         }
       }
     }
    } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ, BKV, 0);  // B = K tile, K-major
-      constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ, D, 1);    // B = V tile, MN-major
+    // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ * NCTA, BKV, 0);  // B = K tile, K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ * NCTA, D, 1);    // B = V tile, MN-major
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t kv_addr = smem_u32(kv_smem);
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (NCTA == 2) umma_commit_2sm(bar); else umma_commit(bar);
+      };
       auto issue_s = [&](int t, int slot) {
         const uint32_t a0 = q_addr + t * TILE_BYTES;
-        const uint32_t b0 = kv_addr + slot * TILE_BYTES;
+        const uint32_t b0 = kv_addr + slot * KV_BYTES;
+        const uint32_t d_tmem = tmem_base + (t ? S_COL1 : S_COL0);
+        if (NCTA == 1 && (p.exp_flags & 1)) {
+          // experiment: the same S tile as two N = 64 halves (keys 0..63 -> columns 0..63, keys 64..127 -> columns 64..127):
+          // does the operand fetch of N = 64 SS MMAs (4 KB of A + 2 KB of B per 32 cycles) keep the tensor pipe fed?
+          constexpr uint32_t idesc_h = make_idesc_bf16_f32(BQ, 64, 0);
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint64_t da = make_smem_desc_sw128(a0 + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+              const uint64_t db = make_smem_desc_sw128(b0 + (kk >> 2) * HALF_BYTES + half * 8192 + (kk & 3) * 32, 16, 1024);
+              umma_ss(d_tmem + half * 64, da, db, idesc_h, kk != 0 ? 1u : 0u);
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-          umma_ss(tmem_base + t * 128, make_smem_desc_sw128(a0 + off, 16, 1024),
-                  make_smem_desc_sw128(b0 + off, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+          // channel slice kk: sub-tile kk / 4 (64 channels each), 32 bytes per 16 channels inside the 128-byte row
+          const uint64_t da = make_smem_desc_sw128(a0 + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b0 + (kk >> 2) * (KV_BYTES / 2) + (kk & 3) * 32, 16, 1024);
+          if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
+          else umma_ss(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
         }
       };
-      auto issue_pv_range = [&](int t, int slot, bool first, int kk0, int kk1) {
-        const uint32_t b0 = kv_addr + slot * TILE_BYTES;
-        for (int kk = kk0; kk < kk1; ++kk) {
-          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8,
-                  make_smem_desc_sw128(b0 + kk * 2048, HALF_BYTES, 1024), idesc_o, (first && kk == 0) ? 0u : 1u);
-        }
-      };
-      // VARIANT 3: the softmax publishes P in two halves (keys 0..63, then 64..127); the first four k-steps of
-      // P V are issued as soon as the first half is in TMEM, overlapping the exps of the second half.
       auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
         mbar_wait(&p_full[t], parity);
         tc_fence_after();
-        if constexpr (VARIANT == 3) {
-          issue_pv_range(t, slot, first, 0, 4);
-          mbar_wait(&p_half[t], parity);
-          tc_fence_after();
-          issue_pv_range(t, slot, first, 4, 8);
-        } else {
-          issue_pv_range(t, slot, first, 0, 8);
+        const uint32_t b0 = kv_addr + slot * KV_BYTES;
+        const uint32_t d_tmem = tmem_base + (t ? O_COL1 : O_COL0);
+        const uint32_t a_tmem = tmem_base + (t ? P_COL1 : P_COL0);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          // 16 keys = 16 rows of 128 bytes; pair: this CTA's 64 channels are ONE swizzle atom (no leading-dim stride)
+          const uint64_t db = make_smem_desc_sw128(b0 + kk * 2048, HALF_BYTES, 1024);
+          const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+          if constexpr (NCTA == 2) umma_ts_2sm(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
+          else umma_ts(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
         }
       };
-      int slot = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++slot == KV_SLOTS) {
-          slot = 0;
-          phase ^= 1;
-        }
+      // Ring items in load order -> item i lives in slot i % KV_SLOTS, phase (i / KV_SLOTS) & 1.
+      //   PIPE 0:  K_0 V_0 K_1 V_1 ...
+      //   PIPE 1:  K_0 K_1 V_0 K_2 V_1 K_3 ... V_{n-3} K_{n-1} V_{n-2} V_{n-1}: K runs TWO tiles ahead of V because S_t(j+2) is
+      //            issued while V_j is in use and a 32 KB TMA load takes ~1000 cycles to land; item i + 5 reuses the slot of
+      //            item i, so K_{j+2} waits for V_{j-2}'s release and V_j for K_{j-1}'s: >= 1.5 key tiles of lead each.
+      auto item_k = [&](int j) { return PIPE ? (j == 0 ? 0 : 2 * j - 1) : 2 * j; };
+      auto item_v = [&](int j) { return PIPE ? min(2 * j + 2, n_kv + j) : 2 * j + 1; };
+      auto wait_item = [&](int item) {
+        mbar_wait(&kv_full[item % KV_SLOTS], (item / KV_SLOTS) & 1);
+        tc_fence_after();
       };
+      auto release_item = [&](int item) { commit(&kv_empty[item % KV_SLOTS]); };
       mbar_wait(q_full, 0);
-      // prologue: S0(0), S1(0)
-      mbar_wait(&kv_full[slot], phase);
-      tc_fence_after();
-      issue_s(0, slot);
-      umma_commit(&s_full[0]);
-      issue_s(1, slot);
-      umma_commit(&s_full[1]);
-      umma_commit(&kv_empty[slot]);
-      advance();
-      for (int j = 0; j < n_kv; ++j) {
-        const int v_slot = slot;
-        const uint32_t v_phase = phase;
-        advance();
-        const int k_slot = slot;  // K_{j+1}
-        const uint32_t k_phase = phase;
-        const bool has_next = (j + 1 < n_kv);
-        if (has_next) advance();
-
-        mbar_wait(&kv_full[v_slot], v_phase);
-        issue_pv(0, v_slot, j == 0, j & 1);
-        umma_commit(&o_done[0]);
-        if (has_next) {
-          mbar_wait(&kv_full[k_slot], k_phase);
+      if constexpr (PIPE == 1) {
+        // Issue order  S1(j+1) PV0(j) S0(j+2) PV1(j): an S only needs the shared S buffer back (the other tile's softmax has
+        // pulled its row into registers), a PV only needs its P.  S_t(j+1) is therefore in TMEM long before softmax_t(j) ends.
+        // The c-th hand-back of the S buffer (S0(0), S1(0), S0(1), S1(1), ...) completes phase c of s_free.
+        uint32_t n_free = 0;
+        auto wait_s_free = [&]() {
+          mbar_wait(s_free, n_free & 1);
+          ++n_free;
           tc_fence_after();
-          issue_s(0, k_slot);
-          umma_commit(&s_full[0]);
+        };
+        wait_item(item_k(0));
+        issue_s(0, item_k(0) % KV_SLOTS);
+        commit(&s_full[0]);
+        wait_s_free();
+        issue_s(1, item_k(0) % KV_SLOTS);
+        commit(&s_full[1]);
+        release_item(item_k(0));
+        if (n_kv > 1) {
+          wait_item(item_k(1));
+          wait_s_free();
+          issue_s(0, item_k(1) % KV_SLOTS);
+          commit(&s_full[0]);
         }
-        issue_pv(1, v_slot, j == 0, j & 1);
-        umma_commit(&o_done[1]);
-        umma_commit(&kv_empty[v_slot]);
-        if (has_next) {
-          issue_s(1, k_slot);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[k_slot]);
+        for (int j = 0; j < n_kv; ++j) {
+          const int v_item = item_v(j);
+          if (j + 1 < n_kv) {
+            wait_s_free();                                   // softmax 0 pulled S0(j+1)
+            issue_s(1, item_k(j + 1) % KV_SLOTS);            // K_{j+1} landed before S0(j+1) was issued
+            commit(&s_full[1]);
+            release_item(item_k(j + 1));
+          }
+          ATTN_STAMP(j, 10);
+          wait_item(v_item);
+          issue_pv(0, v_item % KV_SLOTS, j == 0, j & 1);
+          ATTN_STAMP(j, 11);   // P0 seen ready, PV0 issued
+          commit(&o_done[0]);
+          if (j + 2 < n_kv) {
+            wait_item(item_k(j + 2));
+            ATTN_STAMP(j, 14);
+            wait_s_free();                                   // softmax 1 pulled S1(j+1)
+            ATTN_STAMP(j, 15);
+            issue_s(0, item_k(j + 2) % KV_SLOTS);
+            commit(&s_full[0]);
+          }
+          ATTN_STAMP(j, 12);
+          issue_pv(1, v_item % KV_SLOTS, j == 0, j & 1);
+          ATTN_STAMP(j, 13);   // P1 seen ready, PV1 issued
+          commit(&o_done[1]);
+          release_item(v_item);
+        }
+      } else {
+        // round-1 order  PV0(j) S0(j+1) PV1(j) S1(j+1)  (P_t aliases S_t)
+        wait_item(0);
+        issue_s(0, 0);
+        commit(&s_full[0]);
+        issue_s(1, 0);
+        commit(&s_full[1]);
+        release_item(0);
+        for (int j = 0; j < n_kv; ++j) {
+          const int v_item = 2 * j + 1, k_item = 2 * j + 2;
+          const bool has_next = (j + 1 < n_kv);
+          wait_item(v_item);
+          ATTN_STAMP(j, 10);
+          issue_pv(0, v_item % KV_SLOTS, j == 0, j & 1);
+          ATTN_STAMP(j, 11);   // P0 seen ready, PV0 issued
+          commit(&o_done[0]);
+          if (has_next) {
+            wait_item(k_item);
+            issue_s(0, k_item % KV_SLOTS);
+            commit(&s_full[0]);
+          }
+          ATTN_STAMP(j, 12);
+          issue_pv(1, v_item % KV_SLOTS, j == 0, j & 1);
+          ATTN_STAMP(j, 13);   // P1 seen ready, PV1 issued
+          commit(&o_done[1]);
+          release_item(v_item);
+          if (has_next) {
+            issue_s(1, k_item % KV_SLOTS);
+            commit(&s_full[1]);
+            release_item(k_item);
+          }
         }
       }
     }
@@ -278,304 +434,133 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ softmax warps
     setmaxnreg_inc<REGS_SOFTMAX>();
-    if constexpr (VARIANT == 7) {
-      // VARIANT 7 -- "split-row" softmax.  In variants 1-6 ONE warp owns all 128 key columns of its 32 query rows, so a
-      // tile-step of softmax costs that warp >= 96 MUFU.EX2 instructions x 8 issue cycles = 768 cycles on its SMSP plus
-      // TMEM / barrier latencies (~1400 in total) while the tensor pipe needs only 1024 cycles for the other tile's
-      // PV + S: the pipe idles 28 % of the time (ncu: 72 % active).  Here BOTH warpgroups work on EVERY tile: warp q of
-      // warpgroup 0 takes key columns 0..63 and warp q of warpgroup 1 columns 64..127 of the same 32 rows, tiles are
-      // processed alternately (t = 0, 1, 0, 1, ...), the row maximum is combined through shared memory (one named
-      // barrier of the two warps), the row sum stays split until the epilogue.  Per-tile softmax latency halves.
-      const int half = warp >> 2;   // key-column half of every S tile this warp owns
-      const int quad = warp & 3;    // TMEM lane quadrant (a warp may touch lanes 32 * (warp % 4) .. + 32)
-      const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-      float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [tile][half][128 rows]
-      const int rowi = quad * 32 + lane;
-      const float sl2 = p.scale_log2;
-      float m[2] = {-INFINITY, -INFINITY};
-      float l[2] = {0.f, 0.f};
-      for (int j = 0; j < n_kv; ++j) {
-        const int valid = p.Sk - j * BKV;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t s_addr = tmem_base + lane_base + t * 128;
-          const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
-          mbar_wait(&s_full[t], j & 1);
-          tc_fence_after();
-          uint32_t s[64];
-          tmem_ld_x32(s_addr + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-          tmem_ld_x32(s_addr + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-          tmem_ld_wait();
-          if (valid < BKV) {
-#pragma unroll
-            for (int k = 0; k < 64; ++k)
-              if (half * 64 + k >= valid) s[k] = 0xff800000u;  // -inf
-          }
-          float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-#pragma unroll
-          for (int k = 2; k < 62; k += 4) {
-            mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-          }
-          mx0 = fmax3(mx0, __uint_as_float(s[62]), __uint_as_float(s[63]));
-          const float mx_half = fmaxf(mx0, mx1);
-          // combine with the other half of the row.  The barrier also orders this warp's S loads before the partner's P
-          // stores (P of columns 64..127 lands on the fp32 columns 32..63 that hold the S values of columns 32..63).
-          xch[(t * 2 + half) * 128 + rowi] = mx_half;
-          named_bar_sync(1 + quad, 64);
-          const float mx = fmaxf(mx_half, xch[(t * 2 + (half ^ 1)) * 128 + rowi]);
-          const float m_new = fmaxf(m[t], mx * sl2);
-          if (j == 0) {
-            m[t] = m_new;
-          } else if (__any_sync(0xffffffffu, (m_new - m[t]) > RESCALE_THRESHOLD)) {
-            // same rows, same m_new in both warps of the pair -> same decision; each rescales its 64 columns of O_t
-            const float alpha = fast_exp2(m[t] - m_new);
-            l[t] *= alpha;
-            m[t] = m_new;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld_x32(o_addr + (half * 2 + c) * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-              tmem_st_x32(o_addr + (half * 2 + c) * 32, r);
-            }
-            tmem_st_wait();
-          }
-          const float2 sl2_2 = make_float2(sl2, sl2);
-          const float2 negm_2 = make_float2(-m[t], -m[t]);
-          float2 sum2 = make_float2(0.f, 0.f);
-          uint32_t pk[32];
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int col = c * 32 + 2 * k;
-              const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
-              float2 e;
-              if (k < POLY_PAIRS) {
-                e = exp2_poly2(x);
-              } else {
-                e.x = fast_exp2(x.x);
-                e.y = fast_exp2(x.y);
-              }
-              sum2 = fadd2(sum2, e);
-              pk[c * 16 + k] = pack_bf16x2(e.x, e.y);
-            }
-          }
-          // bf16 P of key columns [64 * half, +64) = 32-bit columns [32 * half, +32) of the S region
-          tmem_st_x32(s_addr + half * 32, pk);
-          l[t] += sum2.x + sum2.y;
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
-        }
-      }
-      // epilogue: O / (l_half0 + l_half1) -> bf16 -> global; each warp stores its 64 of the 128 head channels
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
-        mbar_wait(&o_done[t], (n_kv - 1) & 1);
-        tc_fence_after();
-        xch[(t * 2 + half) * 128 + rowi] = l[t];
-        named_bar_sync(1 + quad, 64);
-        const float inv_l = 1.0f / (l[t] + xch[(t * 2 + (half ^ 1)) * 128 + rowi]);
-        const int row = q_block * (2 * BQ) + t * BQ + rowi;
-        __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
-        if (p.n_peers > 0 && row < p.Sq) {
-          const int d = row / p.rows_per_rank;
-          orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
-                 static_cast<int64_t>(head + p.head_off) * p.o_sh;
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 2 + cc;
-          uint32_t r[32];
-          tmem_ld_x32(o_addr + c * 32, r);
-          tmem_ld_wait();
-          if (row < p.Sq) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
-              o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
-              o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
-              o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
-              reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
-            }
-          }
-        }
-      }
-    } else {
     const int t = warp >> 2;     // query tile
     const int quad = warp & 3;   // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_base + t * 128;
-    const uint32_t o_addr = tmem_base + lane_base + 256 + t * 128;
+    const uint32_t s_addr = tmem_base + lane_base + (t ? S_COL1 : S_COL0);
+    const uint32_t p_addr = tmem_base + lane_base + (t ? P_COL1 : P_COL0);
+    const uint32_t o_addr = tmem_base + lane_base + (t ? O_COL1 : O_COL0);
+    const uint32_t p_full_remote = NCTA == 2 ? mapa_u32(&p_full[t], 0) : 0u;
+    const uint32_t s_free_remote = NCTA == 2 ? mapa_u32(s_free, 0) : 0u;
     const float sl2 = p.scale_log2;
     float m = -INFINITY;  // running max of s * scale_log2 actually used for P
     float l = 0.f;        // running sum of P
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 0);
       const int valid = p.Sk - j * BKV;  // >= 128 except possibly for the last tile
-      if constexpr (VARIANT >= 2) {
-        uint32_t s[128];
-        tmem_ld_x32(s_addr + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
-        tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
-        tmem_ld_wait();
-        if (valid < BKV) {
-#pragma unroll
-          for (int k = 0; k < 128; ++k)
-            if (k >= valid) s[k] = 0xff800000u;  // -inf
-        }
-        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-              mx3 = __uint_as_float(s[3]);
-        if constexpr (VARIANT >= 4) {
-          // FMNMX3: one instruction folds two new values into an accumulator -> 62 instead of 124 max ops per row
-#pragma unroll
-          for (int k = 4; k < 124; k += 8) {
-            mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-            mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-            mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
-            mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
-          }
-          mx0 = fmax3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
-          mx1 = fmax3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
-        } else {
-#pragma unroll
-        for (int k = 4; k < 128; k += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[k]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[k + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[k + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[k + 3]));
-        }
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        const float m_new = fmaxf(m, mx * sl2);
-        if (j == 0) {
-          m = m_new;
-        } else if (__any_sync(0xffffffffu, (m_new - m) > RESCALE_THRESHOLD)) {
-          const float alpha = fast_exp2(m - m_new);
-          l *= alpha;
-          m = m_new;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_x32(o_addr + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-            tmem_st_x32(o_addr + c * 32, r);
-          }
-          tmem_st_wait();
-        }
-        const float2 sl2_2 = make_float2(sl2, sl2);
-        const float2 negm_2 = make_float2(-m, -m);
-        float2 sum2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int col = c * 32 + 2 * k;
-            const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
-            float2 e;
-            constexpr int NPOLY = (VARIANT == 5) ? 2 : ((VARIANT == 6) ? 6 : POLY_PAIRS);
-            if (k < NPOLY) {
-              e = exp2_poly2(x);
-            } else {
-              e.x = fast_exp2(x.x);
-              e.y = fast_exp2(x.y);
-            }
-            sum2 = fadd2(sum2, e);
-            pk[k] = pack_bf16x2(e.x, e.y);
-          }
-          tmem_st_x16(s_addr + c * 16, pk);
-          if (VARIANT == 3 && c == 1) {  // keys 0..63 of P are in TMEM: let the MMA warp start P V
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[t]);
-          }
-        }
-        l += sum2.x + sum2.y;
-      } else {
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(s_addr + c * 32, r);
-        tmem_ld_wait();
-        if (valid >= BKV) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c * 32 + k < valid) mx = fmaxf(mx, __uint_as_float(r[k]));
+      uint32_t s[128];
+      tmem_ld_x32(s_addr + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+      tmem_ld_x32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+      tmem_ld_wait();
+      if constexpr (PIPE == 1) {
+        // the whole row is in registers: hand the shared S buffer back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2 && !leader) mbar_arrive_release_cluster(s_free_remote);
+          else mbar_arrive(s_free);
         }
       }
+      if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 1);
+      if (valid < BKV) {
+#pragma unroll
+        for (int k = 0; k < 128; ++k)
+          if (k >= valid) s[k] = 0xff800000u;  // -inf
+      }
+      // FMNMX3: one instruction folds two new values into an accumulator -> 62 instead of 124 max ops per row
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+            mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int k = 4; k < 124; k += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
+      }
+      mx0 = fmax3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
+      mx1 = fmax3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, mx * sl2);
+      bool o_waited = false;   // PIPE 1: has this warp already seen PV_t(j-1) complete?
       if (j == 0) {
         m = m_new;
-      } else {
-        const bool need = (m_new - m) > RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = fast_exp2(m - m_new);
-          l *= alpha;
-          m = m_new;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld_x32(o_addr + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-            tmem_st_x32(o_addr + c * 32, r);
-          }
-          tmem_st_wait();
+      } else if (__any_sync(0xffffffffu, (m_new - m) > RESCALE_THRESHOLD)) {
+        if constexpr (PIPE == 1) {
+          // O_t is still being accumulated by PV_t(j-1) unless its "O done" phase has completed
+          mbar_wait(&o_done[t], (j - 1) & 1);
+          tc_fence_after();
+          o_waited = true;
         }
-      }
-      // pass 2: P = exp2(s * scale_log2 - m) -> bf16 pairs, written over the first 64 columns of S
-      float lsum = 0.f;
+        const float alpha = fast_exp2(m - m_new);
+        l *= alpha;
+        m = m_new;
 #pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(o_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+          tmem_st_x32(o_addr + c * 32, r);
+        }
+        tmem_st_wait();
+      }
+      if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 2);
+      const float2 sl2_2 = make_float2(sl2, sl2);
+      const float2 negm_2 = make_float2(-m, -m);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t pk[64];
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(s_addr + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float e = fast_exp2(__uint_as_float(r[k]) * sl2 - m);
-          if (valid < BKV && c * 32 + k >= valid) e = 0.f;
-          pv[k] = e;
-          lsum += e;
+        for (int k = 0; k < 16; ++k) {
+          const int col = c * 32 + 2 * k;
+          const float2 x = ffma2(make_float2(__uint_as_float(s[col]), __uint_as_float(s[col + 1])), sl2_2, negm_2);
+          float2 e;
+          if (k < POLY_PAIRS) {
+            e = exp2_poly2(x);
+          } else {
+            e.x = fast_exp2(x.x);
+            e.y = fast_exp2(x.y);
+          }
+          sum2 = fadd2(sum2, e);
+          pk[c * 16 + k] = pack_bf16x2(e.x, e.y);
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(pv[2 * k], pv[2 * k + 1]);
-        // chunk c of S (fp32 columns [32c, 32c+32)) becomes P columns [16c, 16c+16): always inside the
-        // part of S this thread has already consumed.
-        tmem_st_x16(s_addr + c * 16, pk);
+        if constexpr (PIPE == 0) {
+          // chunk c of S (fp32 columns [32c, 32c+32)) becomes P columns [16c, 16c+16): always inside the part of S this
+          // thread has already consumed (the whole row is in registers).
+          tmem_st_x16(p_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+        }
       }
-      l += lsum;
+      l += sum2.x + sum2.y;
+      if constexpr (PIPE == 1) {
+        // P_t(j) goes where PV_t(j-1) reads P_t(j-1): that MMA must have completed (it long has, in steady state)
+        if (j > 0 && !o_waited) {
+          mbar_wait(&o_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_x32(p_addr, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_x32(p_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       }
+      if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 3);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(VARIANT == 3 ? &p_half[t] : &p_full[t]);
+      if (lane == 0) {
+        if (NCTA == 2 && !leader) mbar_arrive_release_cluster(p_full_remote);
+        else mbar_arrive(&p_full[t]);
+      }
+      if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 4);
     }
     // epilogue: O / l -> bf16 -> global
     mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l;
-    const int row = q_block * (2 * BQ) + t * BQ + quad * 32 + lane;
+    const int row = row_base + t * TILE_ROW_STEP + quad * 32 + lane;
     __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
     if (p.n_peers > 0 && row < p.Sq) {
       const int d = row / p.rows_per_rank;
@@ -599,14 +584,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-    }  // variants 1-6
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (NCTA == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -616,7 +600,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
-                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream);
+                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
+                         long long* prof = nullptr, int prof_steps = 0);
+
+// Diagnostics: b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA (0,0,0) written to
+// prof[prof_steps][16] (device memory): columns 0-4 softmax tile 0 (S seen ready, S in registers, row max done, P stores
+// issued, "P ready" arrived), 5-9 the same for tile 1, 10-13 the MMA thread (V tile landed, PV0 issued, S0(j+1) issued, PV1 issued).
+extern "C" int b200_attn_fwd_prof(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                                  int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                                  int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                                  float scale, long long* prof, int prof_steps, void* stream) {
+  if (!prof || prof_steps <= 0) return B200_ERR_ARG;
+  return attn_fwd_impl(q, k, v, o, B, H, Sq, Sk, D, q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss, o_sb, o_sh, o_ss,
+                       scale, nullptr, 0, 0, 0, stream, prof, prof_steps);
+}
 
 extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                              int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
@@ -641,7 +638,8 @@ extern "C" int b200_attn_fwd_scatter(const void* q, const void* k, const void* v
 static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
-                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream) {
+                         float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
+                         long long* prof, int prof_steps) {
   using namespace b200;
   using namespace b200::attn;
   if (!q || !k || !v || !o) return B200_ERR_ARG;
@@ -650,33 +648,34 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   if (H > 65535 || B > 65535) return B200_ERR_SHAPE;
   if ((o_sb % 8) || (o_sh % 8) || (o_ss % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return B200_ERR_ALIGN;
 
-  // B200_ATTN_VARIANT selects the kernel variant for A/B measurements (default DEFAULT_VARIANT):
-  //   1 two-pass bring-up softmax | 2 single pass + f32x2 + 25 % polynomial exp2 | 3 = 2 + split P hand-off
-  //   4 = 2 + FMNMX3 row max | 5 = 4 with 12.5 % polynomial | 6 = 4 with 37.5 %
-  //   7 = split-row softmax: both warpgroups share every tile (64 key columns each), halving the per-tile softmax latency
-  // Measured on B200 (profiles/r01_gpu_session7_attn_ab.log): at 40 heads x 75600^2 every variant >= 2 lands within
-  // 1 % (1213-1228 TFLOP/s) because the run is power-capped (~1.5 GHz); a double-buffered-S design with 64-key steps
-  // was also tried and was no faster, so it was dropped.
-  static int variant = 0;
-  if (variant == 0) {
-    const char* ev = getenv("B200_ATTN_VARIANT");
-    variant = (ev && ev[0] >= '1' && ev[0] <= '7') ? (ev[0] - '0') : DEFAULT_VARIANT;
+  // B200_ATTN_2CTA=1 selects CTA pairs (0 / default: single CTAs); B200_ATTN_PIPE=0 selects the round-1 pipeline (1-CTA
+  // only; the A/B partner), default the decoupled pipeline.  The opt-in to > 48 KB of dynamic shared memory is per device.
+  static int pair_mode = -2, pipe_mode = -2;
+  if (pair_mode == -2) {
+    const char* ev = getenv("B200_ATTN_2CTA");
+    pair_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+    ev = getenv("B200_ATTN_PIPE");
+    pipe_mode = ev ? (ev[0] == '0' ? 0 : 1) : 1;
+  }
+  const bool use_pair = pipe_mode == 1 && (pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && Sq > 2 * BQ));
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B200_ERR_LAUNCH;
+  static bool attr_done[64] = {};
+  if (!attr_done[dev]) {
     bool ok = true;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
-    if (!ok) {
-      variant = 0;
-      return B200_ERR_LAUNCH;
-    }
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+    if (!ok) return B200_ERR_LAUNCH;
+    attr_done[dev] = true;
   }
 
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[4] = {64, 128, 1, 1};
+  const uint32_t box_k_pair[4] = {64, 64, 1, 1};   // pair: each CTA stages 64 of the 128 keys of a K tile
   {
     uint64_t dims[4] = {128, (uint64_t)Sq, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)q_ss, (uint64_t)q_sh, (uint64_t)q_sb};
@@ -686,7 +685,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   {
     uint64_t dims[4] = {128, (uint64_t)Sk, (uint64_t)H, (uint64_t)B};
     uint64_t str[4] = {1, (uint64_t)k_ss, (uint64_t)k_sh, (uint64_t)k_sb};
-    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, box);
+    int rc = make_tmap_bf16(&tmK, k, 4, dims, str, use_pair ? box_k_pair : box);
     if (rc) return rc;
   }
   {
@@ -704,17 +703,47 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.rows_per_rank = rows_per_rank;
   p.head_off = head_off;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
+  p.prof = prof;
+  {
+    static int exp_flags = -1;
+    if (exp_flags < 0) {
+      const char* ev = getenv("B200_ATTN_EXP");
+      exp_flags = ev ? atoi(ev) : 0;
+    }
+    p.exp_flags = exp_flags;
+  }
+  p.prof_steps = prof_steps;
 
-  dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (variant) {
-    case 1: attn_fwd_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 2: attn_fwd_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 3: attn_fwd_kernel<3><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 4: attn_fwd_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 5: attn_fwd_kernel<5><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    case 6: attn_fwd_kernel<6><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
-    default: attn_fwd_kernel<7><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmQ, tmK, tmV, p); break;
+  if (use_pair) {
+    const int pairs = (Sq + 4 * BQ - 1) / (4 * BQ);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, H, B);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1, true>, tmQ, tmK, tmV, p)
+                                : cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1>, tmQ, tmK, tmV, p);
+    if (le != cudaSuccess) {
+      cudaGetLastError();
+      return B200_ERR_LAUNCH;
+    }
+  } else {
+    dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
+    if (pipe_mode == 1) {
+      if (prof) attn_fwd_kernel<1, 1, true><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+      else attn_fwd_kernel<1, 1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    } else {
+      if (prof) attn_fwd_kernel<1, 0, true><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+      else attn_fwd_kernel<1, 0><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    }
   }
   B200_CHECK_LAUNCH();
   return B200_OK;

@@ -140,6 +140,17 @@ int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, in
                           int n_peers, int rows_per_rank, int head_off, int64_t o_sh, int64_t o_ss, float scale,
                           void* stream);
 
+/*
+ * Diagnostics (not a reference call site): b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA
+ * (0,0,0) written to prof[prof_steps][16] (int64, device memory): columns 0-4 softmax of query tile 0 (S seen ready,
+ * S in registers, row max done, P stores issued, "P ready" signalled), 5-9 the same for tile 1, 10-13 the MMA thread
+ * (V tile landed, PV0 issued, S0(j+1) issued, PV1 issued).  Used by scripts/attn_timeline.py; profiles/r02_attn_timeline*.
+ */
+int b200_attn_fwd_prof(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                       int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss, int64_t v_sb,
+                       int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss, float scale,
+                       long long* prof, int prof_steps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Wan 3D-VAE decode (AutoencoderKLWan.decode, vae/wan/model.py:1378; BaseEngine.vae_decode, engine/base_engine.py:2030).
  * Activations are channels-last bf16 [T, H, W, C] (one spatial tile of one video at a time).

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""A/B of one attention kernel variant (B200_ATTN_VARIANT is read once per process): correctness on small / ragged / cross shapes vs
-fp32 math, then the Wan self-attention launch (40 heads x 75600^2) timed with CUDA events."""
+"""A/B of the attention kernel forms (B200_ATTN_2CTA is read once per process: 1 = CTA pairs, 0 = 1-CTA kernel): correctness on
+small / ragged / cross shapes vs fp32 math, then (argument `bench`) the Wan self- and cross-attention launches (40 heads x 75600^2,
+40 x 75600 x 512) timed with CUDA events next to torch SDPA (cuDNN) on the same box."""
 import json
 import math
 import os
@@ -17,8 +18,20 @@ def rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm()).item()
 
 
+def timed(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def main():
-    res = {"variant": os.environ.get("B200_ATTN_VARIANT", "default")}
+    res = {"variant": os.environ.get("B200_ATTN_VARIANT", "default"), "pair": os.environ.get("B200_ATTN_2CTA", "default")}
     for (B, H, Sq, Sk) in [(1, 2, 300, 333), (2, 3, 1000, 777), (1, 32, 1024, 1024), (1, 4, 2048, 512), (1, 2, 128, 64), (1, 1, 4000, 4100)]:
         torch.manual_seed(42)
         q, k, v = (torch.randn(B, H, s, 128, device="cuda", dtype=torch.bfloat16) for s in (Sq, Sk, Sk))
@@ -27,20 +40,20 @@ def main():
         res[f"rel_{B}x{H}x{Sq}x{Sk}"] = round(rel(out, ref), 5)
         res["nan"] = res.get("nan", False) or bool(torch.isnan(out.float()).any())
     if len(sys.argv) > 1 and sys.argv[1] == "bench":
+        sdpa = torch.nn.functional.scaled_dot_product_attention
         q, k, v = (torch.randn(1, 40, 75600, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
         out = ops.attention(q, k, v)
         torch.cuda.synchronize()
-        ref = torch.nn.functional.scaled_dot_product_attention(q[:, :2], k[:, :2], v[:, :2])
+        ref = sdpa(q[:, :2], k[:, :2], v[:, :2])
         res["rel_full_2heads_vs_sdpa"] = round(rel(out[:, :2], ref), 5)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            ops.attention(q, k, v, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        res["ms_40x75600"] = round(ms, 2)
-        res["tflops"] = round(4.0 * 40 * 75600 * 75600 * 128 / ms / 1e9, 1)
+        for name, hs, sk, iters in (("self40", 40, 75600, 8), ("self2", 2, 75600, 20), ("cross40", 40, 512, 50)):
+            qq, kk, vv = q[:, :hs], k[:, :hs, :sk], v[:, :hs, :sk]
+            oo = torch.empty_like(qq)
+            flop = 4.0 * hs * 75600 * sk * 128
+            ms = timed(lambda: ops.attention(qq, kk, vv, out=oo), iters)
+            ms_ref = timed(lambda: sdpa(qq, kk, vv), iters)
+            res[name] = {"ms": round(ms, 3), "tflops": round(flop / ms / 1e9, 1), "sdpa_ms": round(ms_ref, 3),
+                         "sdpa_tflops": round(flop / ms_ref / 1e9, 1)}
     print(json.dumps(res), flush=True)
 
 
