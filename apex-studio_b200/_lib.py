@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapex_b200.so")
+# APEX_B200_LIB: an alternative build of the same library (kernel experiments, scripts/sessions/*); default: the in-tree build
+LIB_PATH = os.environ.get("APEX_B200_LIB") or os.path.join(_HERE, "libapex_b200.so")
 
 _i, _i64, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 

@@ -13,25 +13,37 @@
 //   is still working in registers, and P_t has its own columns.  Issue order  S1(j+1) PV0(j) S0(j+2) PV1(j).  The round-1
 //   layout (S0 | S1 | O0 | O1, P_t aliasing S_t) forced S_t(j+1) behind PV_t(j), which put the whole chain
 //   PV_t(j) -> S_t(j+1) -> softmax_t(j+1) -> "P ready" in series: 512 + 512 + ~1700 + ~290 = 3036 cycles per key tile against
-//   2048 cycles of tensor work (measured with b200_attn_fwd_prof: period 3084, profiles/r02_attn_timeline_*.log).  Decoupled,
-//   the period is max(2048, softmax + ~440).  Hazards: (1) P_t(j+1) may only be stored after PV_t(j) has read P_t(j) ->
-//   the softmax warps wait for "O done"(j) right before their P stores (it has long completed in steady state);
-//   (2) the lazy rescale of O_t (only when the running max grows by more than 2^8) waits for the same barrier.
-// PIPE = 0 -- the round-1 kernel (1-CTA only), kept as the A/B partner (B200_ATTN_PIPE=0).
+//   2048 cycles of tensor work (measured with b200_attn_fwd_prof: period 3084, profiles/r02_attn_timeline_pipe0.log).
+//   Decoupled, the period is 2425 cycles, bound by the hand-over of the single S buffer between the tiles (2 x [S MMAs
+//   512 + "S ready" -> pull ~250 + "S free" -> issue ~300 + queueing behind a PV]).  Hazards: (1) P_t(j+1) may only be stored
+//   after PV_t(j) has read P_t(j) -> the softmax warps wait for "O done"(j) right before their P stores (it has long
+//   completed in steady state); (2) the lazy rescale of O_t (only when the running max grows by more than 2^8) waits for
+//   the same barrier.  Measured (40 heads x 75,600^2, sustained, same box): 1335 TFLOP/s vs 1237 (PIPE 0) vs cuDNN SDPA 1372;
+//   the SM clock settles at 1.30 GHz instead of 1.54 GHz -- the 1 kW power cap converts most of the recovered cycles into a
+//   lower clock (profiles/r02_attn_pipe1_sharedS_ab.log, r02_attn_roles_ab.log).
+//   Tried and rejected, with logs under profiles/: (a) S as two N = 64 MMA groups (64-key double buffering): operand fetch
+//   starves the pipe, r02_attn_exp_n64.log; (b) S two key tiles ahead with P aliasing S and the softmax pulling S(j+1)
+//   before storing P(j) (no hand-back barrier): the extra pull/store chain lengthens every softmax step, 1248-1278 TFLOP/s,
+//   r02_attn_designC_*.log; (c) one issuing thread per MMA stream: the pipe interleaves them and delays S, 1195,
+//   r02_attn_dual_issuer.log; (d) more / fewer polynomial exp2 (12.5 % .. 37.5 %): within 1 %, r02_attn_designC_poly_sweep.log.
+// PIPE = 0 -- the round-1 pipeline (1-CTA only), kept as the A/B partner (B200_ATTN_PIPE=0).
 //
-// NCTA = 2: the CTAs work in PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2).  A pair owns 512 query rows; every
-// MMA is M = 256 (128 rows in each CTA's TMEM).  The B operands are SPLIT across the pair: each CTA stages only 64 of the
-// 128 keys of K_j (S = Q K^T: N = 128 keys, N/2 per CTA) and only 64 of the 128 channels of V_j (O += P V: N = 128
-// channels, N/2 per CTA), so every K/V byte is fetched from L2 and written to shared memory once per 512 query rows
+// NCTA = 2 (opt-in, B200_ATTN_2CTA=1): the CTAs work in PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2).  A pair owns
+// 512 query rows; every MMA is M = 256 (128 rows in each CTA's TMEM).  The B operands are SPLIT across the pair: each CTA
+// stages only 64 of the 128 keys of K_j (S = Q K^T: N = 128 keys, N/2 per CTA) and only 64 of the 128 channels of V_j (O += P V:
+// N = 128 channels, N/2 per CTA), so every K/V byte is fetched from L2 and written to shared memory once per 512 query rows
 // instead of once per 256, and the operand reads of the tensor pipe drop from 192 KB to 128 KB per key tile per SM.  Both
 // CTAs' TMA bytes complete on the LEADER's mbarrier; the leader's single MMA thread issues for both;
 // tcgen05.commit.multicast publishes "S ready", "O done" and "slot free" in both CTAs; the peer's softmax warps signal
-// "S free" / "P ready" on the leader's barriers through remote (shared::cluster) arrives.
+// "S free" / "P ready" on the leader's barriers through remote (shared::cluster) arrives.  Correct on every test shape, but
+// SLOWER (1029-1080 TFLOP/s): the remote arrives and multicast commits add ~400 cycles to hand-overs that sit on the
+// critical path of this kernel (unlike the GEMM, where the pair gained 10 %), so single CTAs stay the default.
 //
 // Replaces attention_register.call(q, k, v) -- attention/functions.py:84 (`sdpa` :338-377 is the gold
 // backend) as called by transformer/wan/base/attention.py:397.
 #include "host_util.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 #include "sm100_ptx.cuh"
 
@@ -43,7 +55,13 @@ constexpr int BQ = 128;   // rows per query tile (per CTA)
 constexpr int BKV = 128;  // keys per tile
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two [128 x 64] swizzled half tiles
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr int NUM_THREADS = 384;  // warpgroups: softmax0 | softmax1 | {TMA, MMA, 2 idle warps}
+// warpgroups: softmax0 | softmax1 | {TMA, MMA issuer, 2 idle warps}.  The single-thread roles park their mbarrier waits in
+// hardware (mbar_wait_parked) instead of re-polling.  (Roles in warps 0-3 vs 8-11, parked vs polling waits: all four combinations
+// measure the same, 1332-1336 TFLOP/s, profiles/r02_attn_roles_ab.log.)
+constexpr int NUM_THREADS = 384;
+constexpr int ROLE_WG = 2;          // warpgroup of the single-thread roles
+constexpr int TMA_WARP = 4 * ROLE_WG, MMA_WARP = 4 * ROLE_WG + 1;
+B200_DEVICE void role_wait(uint64_t* bar, uint32_t parity) { mbar_wait_parked(bar, parity); }
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 // setmaxnreg budget.  The CTA owns 168 regs x 384 threads = 504 per (softmax0, softmax1, other) warp triple; the
 // increase BLOCKS until the pool has enough registers, so 2 * REGS_SOFTMAX + REGS_OTHER must not exceed 504
@@ -73,7 +91,6 @@ struct Params {
   int n_peers;        // 0 = plain store into `o`
   int rows_per_rank;  // S / P
   int head_off;       // first global head computed by this rank
-  int exp_flags;      // experiments (B200_ATTN_EXP): bit 0 = issue every S tile as two N = 64 MMA groups
   long long* prof;    // PROF kernels only: [steps][16] SM-clock timestamps of CTA (0,0,0) (b200_attn_fwd_prof)
   int prof_steps;
 };
@@ -128,11 +145,14 @@ B200_DEVICE float fmax3(float a, float b, float c) {
   return r;
 }
 
-constexpr int POLY_PAIRS = 4;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
+#ifndef ATTN_POLY_PAIRS
+#define ATTN_POLY_PAIRS 4
+#endif
+constexpr int POLY_PAIRS = ATTN_POLY_PAIRS;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
 
 #define ATTN_STAMP(step, k)                                                                     \
   do {                                                                                         \
-    if (PROF && prof_cta && (step) < p.prof_steps) p.prof[(step) * 16 + (k)] = clock64();       \
+    if (PROF && prof_cta && (step) < p.prof_steps) p.prof[(step) * 32 + (k)] = clock64();       \
   } while (0)
 
 template <int NCTA, int PIPE, bool PROF = false>
@@ -188,7 +208,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(s_free, 4 * NCTA);
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     if constexpr (NCTA == 2) {
       tmem_alloc_2sm(tmem_ptr, 512);
       tmem_relinquish_2sm();
@@ -206,9 +226,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 88.
   // (one setmaxnreg per warpgroup, executed by all four of its warps at the same instruction, at the top of the
   // warpgroup's branch so that ptxas budgets the branch accordingly.)
-  if (warp >= 8) {
+  if ((warp >> 2) == ROLE_WG) {
    setmaxnreg_dec<REGS_OTHER>();
-   if (warp == 8) {
+   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer (every CTA stages its own part)
     if (elect_one()) {
       if constexpr (NCTA == 2) {
@@ -227,7 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t phase = 0;
         const int r64 = static_cast<int>(cta_rank) * 64;
         auto load_k = [&](int j) {   // K_j: this CTA's 64 keys x 128 channels = two [64 x 64] swizzled sub-tiles
-          mbar_wait(&kv_empty[slot], phase ^ 1);
+          role_wait(&kv_empty[slot], phase ^ 1);
           uint8_t* dst = kv_smem + slot * KV_BYTES;
           const uint32_t fbar = mapa_u32(&kv_full[slot], 0);
           if (leader) mbar_arrive_expect_tx(&kv_full[slot], 2 * KV_BYTES);
@@ -236,7 +256,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
         };
         auto load_v = [&](int j) {   // V_j: all 128 keys x this CTA's 64 channels = one [128 x 64] swizzled half tile
-          mbar_wait(&kv_empty[slot], phase ^ 1);
+          role_wait(&kv_empty[slot], phase ^ 1);
           uint8_t* dst = kv_smem + slot * KV_BYTES;
           const uint32_t fbar = mapa_u32(&kv_full[slot], 0);
           if (leader) mbar_arrive_expect_tx(&kv_full[slot], 2 * KV_BYTES);
@@ -259,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         int slot = 0;
         uint32_t phase = 0;
         auto load_tile = [&](const CUtensorMap* tm, int j) {
-          mbar_wait(&kv_empty[slot], phase ^ 1);
+          role_wait(&kv_empty[slot], phase ^ 1);
           uint8_t* dst = kv_smem + slot * KV_BYTES;
           mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
           tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV, head, batch);
@@ -281,7 +301,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-   } else if (warp == 9) {
+   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if (leader && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ * NCTA, BKV, 0);  // B = K tile, K-major
@@ -295,20 +315,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t a0 = q_addr + t * TILE_BYTES;
         const uint32_t b0 = kv_addr + slot * KV_BYTES;
         const uint32_t d_tmem = tmem_base + (t ? S_COL1 : S_COL0);
-        if (NCTA == 1 && (p.exp_flags & 1)) {
-          // experiment: the same S tile as two N = 64 halves (keys 0..63 -> columns 0..63, keys 64..127 -> columns 64..127):
-          // does the operand fetch of N = 64 SS MMAs (4 KB of A + 2 KB of B per 32 cycles) keep the tensor pipe fed?
-          constexpr uint32_t idesc_h = make_idesc_bf16_f32(BQ, 64, 0);
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int kk = 0; kk < D / 16; ++kk) {
-              const uint64_t da = make_smem_desc_sw128(a0 + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
-              const uint64_t db = make_smem_desc_sw128(b0 + (kk >> 2) * HALF_BYTES + half * 8192 + (kk & 3) * 32, 16, 1024);
-              umma_ss(d_tmem + half * 64, da, db, idesc_h, kk != 0 ? 1u : 0u);
-            }
-          }
-          return;
-        }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           // channel slice kk: sub-tile kk / 4 (64 channels each), 32 bytes per 16 channels inside the 128-byte row
@@ -319,7 +325,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       };
       auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
-        mbar_wait(&p_full[t], parity);
+        role_wait(&p_full[t], parity);
         tc_fence_after();
         const uint32_t b0 = kv_addr + slot * KV_BYTES;
         const uint32_t d_tmem = tmem_base + (t ? O_COL1 : O_COL0);
@@ -341,21 +347,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       auto item_k = [&](int j) { return PIPE ? (j == 0 ? 0 : 2 * j - 1) : 2 * j; };
       auto item_v = [&](int j) { return PIPE ? min(2 * j + 2, n_kv + j) : 2 * j + 1; };
       auto wait_item = [&](int item) {
-        mbar_wait(&kv_full[item % KV_SLOTS], (item / KV_SLOTS) & 1);
+        role_wait(&kv_full[item % KV_SLOTS], (item / KV_SLOTS) & 1);
         tc_fence_after();
       };
       auto release_item = [&](int item) { commit(&kv_empty[item % KV_SLOTS]); };
-      mbar_wait(q_full, 0);
       if constexpr (PIPE == 1) {
         // Issue order  S1(j+1) PV0(j) S0(j+2) PV1(j): an S only needs the shared S buffer back (the other tile's softmax has
         // pulled its row into registers), a PV only needs its P.  S_t(j+1) is therefore in TMEM long before softmax_t(j) ends.
         // The c-th hand-back of the S buffer (S0(0), S1(0), S0(1), S1(1), ...) completes phase c of s_free.
+        // (Two issuing threads -- one per stream -- were tried: the pipe interleaves their MMAs, an S group then takes ~1000
+        // instead of ~600 cycles from issue to "S ready", and S is the stream on the critical path: 1195 vs 1330 TFLOP/s,
+        // profiles/r02_attn_dual_issuer.log.)
         uint32_t n_free = 0;
         auto wait_s_free = [&]() {
-          mbar_wait(s_free, n_free & 1);
+          role_wait(s_free, n_free & 1);
           ++n_free;
           tc_fence_after();
         };
+        role_wait(q_full, 0);
         wait_item(item_k(0));
         issue_s(0, item_k(0) % KV_SLOTS);
         commit(&s_full[0]);
@@ -398,6 +407,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       } else {
         // round-1 order  PV0(j) S0(j+1) PV1(j) S1(j+1)  (P_t aliases S_t)
+        role_wait(q_full, 0);
         wait_item(0);
         issue_s(0, 0);
         commit(&s_full[0]);
@@ -430,7 +440,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-   }  // warps 10, 11 of the third warpgroup idle until the final barrier
+   }  // the remaining warps of this warpgroup idle until the final barrier
   } else {
     // ------------------------------------------------------------------ softmax warps
     setmaxnreg_inc<REGS_SOFTMAX>();
@@ -445,7 +455,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float sl2 = p.scale_log2;
     float m = -INFINITY;  // running max of s * scale_log2 actually used for P
     float l = 0.f;        // running sum of P
-    for (int j = 0; j < n_kv; ++j) {
+    // One key tile.  MASKED is a compile-time flag: only the LAST tile can be partial (Sk % 128 != 0); written as a run-time
+    // `if` the compiler turned the masking into 128 ISETP + 128 SEL executed for EVERY tile -- 30 % of the loop's instructions.
+    auto step = [&](const int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 0);
@@ -466,7 +479,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 1);
-      if (valid < BKV) {
+      if constexpr (MASKED) {
 #pragma unroll
         for (int k = 0; k < 128; ++k)
           if (k >= valid) s[k] = 0xff800000u;  // -inf
@@ -555,7 +568,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         else mbar_arrive(&p_full[t]);
       }
       if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 4);
-    }
+    };
+    const int n_full = p.Sk / BKV;   // key tiles without a tail
+    for (int j = 0; j < n_full; ++j) step(j, std::false_type{});
+    if (n_full < n_kv) step(n_kv - 1, std::true_type{});
     // epilogue: O / l -> bf16 -> global
     mbar_wait(&o_done[t], (n_kv - 1) & 1);
     tc_fence_after();
@@ -588,7 +604,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 9) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     if constexpr (NCTA == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
@@ -604,7 +620,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
                          long long* prof = nullptr, int prof_steps = 0);
 
 // Diagnostics: b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA (0,0,0) written to
-// prof[prof_steps][16] (device memory): columns 0-4 softmax tile 0 (S seen ready, S in registers, row max done, P stores
+// prof[prof_steps][32] (device memory): columns 0-4 softmax tile 0 (S seen ready, S in registers, row max done, P stores
 // issued, "P ready" arrived), 5-9 the same for tile 1, 10-13 the MMA thread (V tile landed, PV0 issued, S0(j+1) issued, PV1 issued).
 extern "C" int b200_attn_fwd_prof(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                                   int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
@@ -704,15 +720,6 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.head_off = head_off;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
   p.prof = prof;
-  {
-    static int exp_flags = -1;
-    if (exp_flags < 0) {
-      const char* ev = getenv("B200_ATTN_EXP");
-      exp_flags = ev ? atoi(ev) : 0;
-    }
-    p.exp_flags = exp_flags;
-  }
-  p.prof_steps = prof_steps;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use_pair) {

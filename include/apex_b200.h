@@ -142,7 +142,7 @@ int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, in
 
 /*
  * Diagnostics (not a reference call site): b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA
- * (0,0,0) written to prof[prof_steps][16] (int64, device memory): columns 0-4 softmax of query tile 0 (S seen ready,
+ * (0,0,0) written to prof[prof_steps][32] (int64, device memory): columns 0-4 softmax of query tile 0 (S seen ready,
  * S in registers, row max done, P stores issued, "P ready" signalled), 5-9 the same for tile 1, 10-13 the MMA thread
  * (V tile landed, PV0 issued, S0(j+1) issued, PV1 issued).  Used by scripts/attn_timeline.py; profiles/r02_attn_timeline*.
  */

@@ -20,7 +20,7 @@ def main():
     lib = _lib.load()
     q, k, v = (torch.randn(1, H, S, 128, device="cuda", dtype=torch.bfloat16) for _ in range(3))
     o = torch.empty_like(q)
-    prof = torch.zeros(steps, 16, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(steps, 32, dtype=torch.int64, device="cuda")
     st = lambda t: [t.stride(0), t.stride(1), t.stride(2)]
     for _ in range(2):
         rc = lib.b200_attn_fwd_prof(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), 1, H, S, S, 128, *st(q), *st(k), *st(v),
@@ -31,8 +31,10 @@ def main():
         raw = prof.cpu()[200:204]
         base = int(raw[0, 0])
         names = ["t0:S_seen", "t0:S_in_regs", "t0:max_done", "t0:P_stored", "t0:P_arrived", "t1:S_seen", "t1:S_in_regs", "t1:max_done",
-                 "t1:P_stored", "t1:P_arrived", "mma:pre_PV0", "mma:PV0_issued", "mma:pre_PV1", "mma:PV1_issued", "mma:K_landed", "mma:S_free_seen"]
-        ev = sorted((int(raw[r, c]) - base, f"j={200 + r} {names[c]}") for r in range(4) for c in range(16) if int(raw[r, c]))
+                 "t1:P_stored", "t1:P_arrived", "mma:pre_PV0", "mma:PV0_issued", "mma:pre_PV1", "mma:PV1_issued", "mma:K_landed", "mma:S_free_seen",
+                 "t0w0:P_arrived", "t0w1:P_arrived", "t0w2:P_arrived", "t0w3:P_arrived", "t1w0:P_arrived", "t1w1:P_arrived", "t1w2:P_arrived",
+                 "t1w3:P_arrived", "mma:V_landed(0)", "mma:P0_seen", "mma:V_landed(1)", "mma:P1_seen"] + ["?"] * 4
+        ev = sorted((int(raw[r, c]) - base, f"j={200 + r} {names[c]}") for r in range(4) for c in range(32) if int(raw[r, c]))
         for tt, nm in ev:
             print(f"{tt:7d}  {nm}", flush=True)
     t = prof.cpu().double()[100:380]          # steady state

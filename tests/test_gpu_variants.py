@@ -1,6 +1,6 @@
-"""Opt-in kernel variants stay correct: the selection environment variables are read once per process, so each variant runs in
-a subprocess.  Covered: attention variant 7 (split-row softmax) and 4 (FMNMX3 row max), the 1-CTA GEMM for large M
-(B200_LINEAR_2CTA=0) and the 128x64 small-M GEMM form (B200_LINEAR_SMALLM=1).  Bars: attention rel-L2 <= 5e-3 vs fp32 math,
+"""Opt-in kernel forms stay correct: the selection environment variables are read once per process, so each form runs in
+a subprocess.  Covered: the attention A/B partners -- the round-1 pipeline (B200_ATTN_PIPE=0) and the CTA-pair form
+(B200_ATTN_2CTA=1) --, the 1-CTA GEMM for large M (B200_LINEAR_2CTA=0) and the 128x64 small-M GEMM form (B200_LINEAR_SMALLM=1).  Bars: attention rel-L2 <= 5e-3 vs fp32 math,
 GEMM rel-L2 <= 4e-3 vs fp32 math of the same bf16 operands."""
 import json
 import os
@@ -44,10 +44,10 @@ def _run(cmd, env):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("variant", ["4", "7"])
-def test_attention_variant_in_subprocess(variant):
-    res = _run([sys.executable, os.path.join(ROOT, "scripts", "attn_variant_ab.py")], {"B200_ATTN_VARIANT": variant})
-    assert res["variant"] == variant and res["nan"] is False
+@pytest.mark.parametrize("env", [{"B200_ATTN_PIPE": "0"}, {"B200_ATTN_2CTA": "1"}, {"B200_ATTN_PIPE": "1", "B200_ATTN_2CTA": "0"}])
+def test_attention_form_in_subprocess(env):
+    res = _run([sys.executable, os.path.join(ROOT, "scripts", "attn_variant_ab.py")], env)
+    assert res["nan"] is False
     errs = {k: v for k, v in res.items() if k.startswith("rel_")}
     assert len(errs) == 6 and all(v <= 5e-3 for v in errs.values()), errs
 
