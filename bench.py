@@ -9,7 +9,8 @@ One "step" = what `moe_denoise` does per timestep (apps/api/src/engine/wan/share
 conditional and the unconditional DiT forward over latents [1,16,21,90,160] (S = 75,600 tokens, 40 layers,
 d = 5120, 40 heads x 128, ffn 13,824, 512 text tokens), the CFG combine and the UniPC scheduler step.
 Synthetic latents / text embeddings / random-init bf16 weights of the A14B architecture (both experts
-resident); the first W+K timesteps of a 50-step schedule are run (all in the high-noise expert's range).
+resident); the first W+K(+e2e) timesteps of a 50-step schedule are run (with shift 3 only the first ~15 timesteps are
+>= 875, so a longer run crosses the high-noise -> low-noise expert switch; both experts are resident either way).
 
 Printed JSON (one line, rank 0): `value` = steps/sec with inputs resident in HBM (CUDA events, max over ranks);
 `e2e` = the same step driven from HOST buffers through the public API (pinned-host -> device copy of latents
@@ -22,6 +23,7 @@ N > 1: CFG pair x token/head shards (apex-studio_b200/parallel.py); strong scali
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -303,6 +305,10 @@ def run_b200_arm(args):
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
 
+    # result checksum: the fp32 latents after the W + K device-resident steps, byte for byte.  Every N runs the same seeded
+    # job, so the N = 1 / 2 / 4 / 8 lines of a scaling run can be compared for the claimed bit-identity of the sharded paths.
+    latents_sha = hashlib.sha256(state["latents"].detach().float().cpu().contiguous().numpy().tobytes()).hexdigest()
+
     attn_ms = [s.elapsed_time(e) for s, e, _, _ in attn_events]
     heads_per_launch = attn_events[0][2] if attn_events else HEADS
     attn_avg = statistics.mean(attn_ms) if attn_ms else float("nan")
@@ -344,7 +350,8 @@ def run_b200_arm(args):
             vae_info = {"ms": vae_ms, "frames": int(frames.shape[2]), "frames_per_sec": frames.shape[2] / (vae_ms * 1e-3),
                         "tiles": len(vae.tile_grid(LATENT_SHAPE[3], LATENT_SHAPE[4])), "launches": vae_launches,
                         "algorithmic_tflops_untiled": 6.39e14 / (vae_ms * 1e-3) / 1e12,
-                        "finite": bool(torch.isfinite(frames.float()).all().item())}
+                        "finite": bool(torch.isfinite(frames.float()).all().item()),
+                        "frames_sha256": hashlib.sha256(frames.detach().view(torch.int16).cpu().contiguous().numpy().tobytes()).hexdigest()}
         except Exception as e:  # the DiT line must survive a VAE problem
             vae_info = {"error": repr(e)[:300]}
 
@@ -390,6 +397,7 @@ def run_b200_arm(args):
         "e2e": {"value": 1000.0 / e2e_ms_step, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms_step},
         "gpu_launches": launches, "clocks": clocks,
+        "latents_sha256": latents_sha, "latents_sha256_of": f"fp32 latents after {args.warmup + args.steps} steps (seeded; identical for every N)",
         "frames_per_sec_50step_denoise_only": 81.0 / (50 * ms_step * 1e-3),
         "vae_decode": vae_info,
         "frames_per_sec": (81.0 / (50 * ms_step * 1e-3 + vae_info["ms"] * 1e-3)) if (vae_info and "ms" in vae_info) else None,
