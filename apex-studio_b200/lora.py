@@ -5,7 +5,13 @@ calls ``model.load_lora_adapter(state_dict, adapter_name=..., prefix=..., metada
 ``model.set_adapters(names, weights=scales)``; PEFT injects ``lora_A`` / ``lora_B`` modules, so every adapted
 ``nn.Linear`` costs two extra skinny GEMMs, an elementwise scale and an add per call, each rounding to bf16:
 
-    y = W x + b + scaling * B (A x)            scaling = weight * lora_alpha / r,   lora_alpha = r (manager.py:444-447)
+    y = W x + b + scaling * B (A x)            scaling = weight * alpha_m / r_m
+
+with ``alpha_m = alpha_pattern.get(m, lora_alpha)`` and ``r_m = rank_pattern.get(m, r)`` per target module m (PEFT
+``LoraLayer.update_layer``).  The manager's metadata (manager.py:433-447) sets ``r = lora_alpha =`` the MOST COMMON rank of the
+file and lists the other ranks in ``rank_pattern``, so a module whose rank differs from the modal rank is scaled by
+``r_modal / r_m`` -- reproduced here (``peft_scaling``), from the metadata when it is passed, else recomputed the way the
+manager computes it.
 
 Here the adapters never touch the per-step path.  ``set_adapters`` rebuilds the effective weight of every adapted
 projection once, on the device, with ONE launch of ``b200_linear`` per projection:
@@ -45,6 +51,7 @@ class LoraAdapter:
     B: Dict[str, torch.Tensor] = field(default_factory=dict)
     bias: Dict[str, torch.Tensor] = field(default_factory=dict)
     rank: Dict[str, int] = field(default_factory=dict)
+    scaling: Dict[str, float] = field(default_factory=dict)   # PEFT's alpha_m / r_m per module (1.0 at the modal rank)
 
     @property
     def modules(self) -> List[str]:
@@ -131,6 +138,41 @@ def split_modules(state: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.T
     return mods
 
 
+def _pattern_get(pattern: Optional[dict], module: str, default):
+    """PEFT looks a module up in ``rank_pattern`` / ``alpha_pattern`` by exact name or by name suffix."""
+    if not pattern:
+        return default
+    if module in pattern:
+        return pattern[module]
+    for key, val in pattern.items():
+        if module.endswith("." + key):
+            return val
+    return default
+
+
+def peft_scaling(ranks: Dict[str, int], metadata: Optional[dict] = None) -> Tuple[Dict[str, float], dict]:
+    """Per-module ``alpha_m / r_m`` as PEFT computes it from the LoraConfig the manager builds (manager.py:433-447):
+    without explicit metadata ``r = lora_alpha =`` the most common rank (first seen wins a tie, as
+    ``collections.Counter.most_common`` does) and ``rank_pattern`` holds the other ranks.  Returns (scaling, config)."""
+    import collections
+
+    md = dict(metadata or {})
+    if "r" not in md or "lora_alpha" not in md:
+        r_modal = collections.Counter(ranks.values()).most_common(1)[0][0]
+        md.setdefault("r", int(r_modal))
+        md.setdefault("lora_alpha", int(md["r"]))
+        md.setdefault("rank_pattern", {m: rr for m, rr in ranks.items() if rr != md["r"]})
+        md.setdefault("alpha_pattern", {})
+    scaling = {}
+    for m, r_actual in ranks.items():
+        r_m = int(_pattern_get(md.get("rank_pattern"), m, md["r"]))
+        if r_m != r_actual:
+            raise ValueError(f"LoRA module {m}: metadata says rank {r_m}, the factors have rank {r_actual}")
+        alpha_m = float(_pattern_get(md.get("alpha_pattern"), m, md["lora_alpha"]))
+        scaling[m] = alpha_m / r_m
+    return scaling, md
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the mixin
 # ---------------------------------------------------------------------------------------------------------
@@ -178,9 +220,9 @@ class LoraHostMixin:
             ad.rank[module] = int(d["A"].shape[0])
         if not ad.A:
             raise ValueError("no LoRA weights found for this model in the state dict")
+        ad.scaling, cfg = peft_scaling(ad.rank, metadata)
         adapters[adapter_name] = ad
-        ranks = sorted(set(ad.rank.values()))
-        self.peft_config[adapter_name] = dict(metadata or {}, r=ranks[-1], target_modules=ad.modules)
+        self.peft_config[adapter_name] = dict(cfg, target_modules=ad.modules)
         self._lora_scales.setdefault(adapter_name, 1.0)
 
     def set_adapters(self, adapter_names: Union[str, Sequence[str]],
@@ -253,7 +295,8 @@ class LoraHostMixin:
             w_rows.copy_(base_w, non_blocking=True)
             if base_b is not None:
                 self.w[bkey][row0:row0 + rows].copy_(base_b, non_blocking=True)
-            parts = [] if self._lora_disabled else [(ad, self._lora_scales.get(n, 0.0)) for n, ad in adapters.items()
+            parts = [] if self._lora_disabled else [(ad, self._lora_scales.get(n, 0.0) * ad.scaling.get(module, 1.0))
+                                                    for n, ad in adapters.items()
                                                     if module in ad.A and self._lora_scales.get(n, 0.0) != 0.0]
             if not parts:
                 continue

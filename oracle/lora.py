@@ -6,8 +6,10 @@ The reference applies LoRAs through PEFT (apps/api/src/lora/manager.py:566-588: 
 their published arithmetic:
 
   peft.tuners.lora.layer.Linear.forward :  result = base_layer(x);  result = result + lora_B(lora_A(dropout(x))) * scaling
-  diffusers set_adapters -> LoraLayer.set_scale :  scaling[adapter] = weight * lora_alpha / r
-  manager.py:444-447 :  lora_alpha = r for every adapter, so  scaling = weight
+  diffusers set_adapters -> LoraLayer.set_scale :  scaling[adapter] = weight * alpha_m / r_m   (per module m:
+      r_m = rank_pattern.get(m, r), alpha_m = alpha_pattern.get(m, lora_alpha) -- peft LoraLayer.update_layer)
+  manager.py:433-447 :  r = lora_alpha = the MOST COMMON rank of the file, rank_pattern = the other ranks, so
+      scaling_m = weight * r_modal / r_m   (= weight for single-rank files)        -> :func:`manager_scaling`
 
 PARITY UNPINNED: the reference holds no test or golden vector for LoRA numerics (tests/ only check LoRA *resolution*).
 """
@@ -19,6 +21,14 @@ import torch
 import torch.nn.functional as F
 
 Weights = Dict[str, torch.Tensor]
+
+
+def manager_scaling(ranks: Dict[str, int]) -> Dict[str, float]:
+    """manager.py:433-447 + peft: per-module alpha / r with lora_alpha = r = most common rank (first seen wins ties)."""
+    import collections
+
+    r_modal = collections.Counter(ranks.values()).most_common(1)[0][0]
+    return {m: r_modal / r for m, r in ranks.items()}
 
 
 def lora_linear_runtime(x: torch.Tensor, weight: torch.Tensor, bias, adapters: Sequence[Tuple[torch.Tensor, torch.Tensor, float]]):

@@ -81,6 +81,23 @@ def test_lora_target_resolves_fused_projections():
         m.set_adapters(["a"], [1.0])
 
 
+def test_mixed_rank_scaling_follows_the_managers_peft_config():
+    """manager.py:433-447: r = lora_alpha = the modal rank, rank_pattern for the rest -> PEFT scales a module of rank r_m
+    by r_modal / r_m.  Host logic only (no GPU)."""
+    from apex_studio_b200.lora import peft_scaling
+
+    ranks = {"a.to_q": 16, "a.to_k": 16, "a.to_v": 4, "b.ffn": 32, "b.to_out.0": 16}
+    sc, cfg = peft_scaling(ranks)
+    assert cfg["r"] == 16 and cfg["lora_alpha"] == 16 and cfg["rank_pattern"] == {"a.to_v": 4, "b.ffn": 32}
+    assert sc == {"a.to_q": 1.0, "a.to_k": 1.0, "a.to_v": 4.0, "b.ffn": 0.5, "b.to_out.0": 1.0}
+    assert sc == lora_oracle.manager_scaling(ranks)
+    # explicit metadata (what the manager passes to load_lora_adapter) wins, incl. alpha_pattern and suffix matching
+    sc2, _ = peft_scaling(ranks, {"r": 16, "lora_alpha": 8, "rank_pattern": {"to_v": 4, "b.ffn": 32}, "alpha_pattern": {"b.ffn": 64}})
+    assert sc2 == {"a.to_q": 0.5, "a.to_k": 0.5, "a.to_v": 2.0, "b.ffn": 2.0, "b.to_out.0": 0.5}
+    with pytest.raises(ValueError):
+        peft_scaling(ranks, {"r": 16, "lora_alpha": 16, "rank_pattern": {}})      # to_v is rank 4, metadata says 16
+
+
 def test_oracle_runtime_form_equals_merged_weight():
     g = torch.Generator().manual_seed(3)
     x, W, b = torch.randn(5, 16, generator=g), torch.randn(12, 16, generator=g), torch.randn(12, generator=g)
@@ -171,3 +188,64 @@ def test_two_adapters_forward_vs_oracle_runtime_form():
     m.disable_lora()
     out0 = m(lat.to(DEV, torch.bfloat16), t.to(DEV), text.to(DEV, torch.bfloat16), return_dict=False)[0]
     assert rel_l2(out0, torch.from_numpy(g["out_bf16"])) <= 2e-2
+
+
+@pytest.mark.gpu
+def test_mixed_rank_adapter_merge_uses_per_module_scaling():
+    """One adapter file with ranks 16 / 16 / 4 (modal rank 16): the rank-4 module must be merged with 4x the weight
+    (PEFT: lora_alpha / r_m = 16 / 4), the rank-16 modules with 1x."""
+    m, w32 = _model()
+    mods = ["blocks.0.attn1.to_q", "blocks.0.attn1.to_k", "blocks.0.attn1.to_v"]
+    lo = {}
+    for mod, r in zip(mods, (16, 16, 4)):
+        lo.update(lora_oracle.make_lora(w32, [mod], rank=r, seed=r + len(mod)))
+    m.load_lora_adapter(lo, adapter_name="mixed", prefix=None)
+    assert m.peft_config["mixed"]["r"] == 16 and m.peft_config["mixed"]["rank_pattern"] == {"blocks.0.attn1.to_v": 4}
+    m.set_adapters(["mixed"], [0.5])
+    sc = lora_oracle.manager_scaling({mod: r for mod, r in zip(mods, (16, 16, 4))})
+    for mod in mods:
+        wkey, r0, rows, _ = m.lora_target(mod)
+        got = m.w[wkey][r0:r0 + rows].float().cpu()
+        exact = lora_oracle.merged_weight(w32[mod + ".weight"], [(lo[mod + ".lora_A.weight"], lo[mod + ".lora_B.weight"], 0.5 * sc[mod])])
+        wrong = lora_oracle.merged_weight(w32[mod + ".weight"], [(lo[mod + ".lora_A.weight"], lo[mod + ".lora_B.weight"], 0.5)])
+        assert rel_l2(got, exact) <= 4e-3
+        if sc[mod] != 1.0:
+            assert rel_l2(got, wrong) > 2e-2
+
+
+@pytest.mark.gpu
+def test_merged_bf16_weight_vs_peft_runtime_form_small_delta():
+    """Quantifies what merging costs against PEFT's runtime form  y = W x + s B (A x)  for a SMALL-delta adapter (the
+    regime where rounding W + s B A to bf16 loses most of the delta): relative L2 of the adapter's *contribution*
+    (y - W x) reproduced by the merged weight, next to the same figure for the runtime form evaluated in bf16 as PEFT does
+    (A x, B(.), the scale and the sum each round the activation).  Expected from the CPU emulation of both forms: |delta| ~
+    2^-9 |W| (half a bf16 ulp of the weight): merged 0.61 vs runtime 1.05; |delta| ~ 2^-5 |W|: merged 0.052 vs runtime 0.074;
+    output-level error merged 1.2e-3 / 1.7e-3 vs runtime 2.1e-3 / 2.3e-3.  Stated bars: the merged form is at least as close
+    to exact as the runtime form on both measures, contribution error <= 0.7 (tiny) / 0.06 (small), output error <= 2.5e-3."""
+    torch.manual_seed(0)
+    N, K, r = 512, 512, 16
+    W = (torch.randn(N, K) * 0.02).bfloat16()
+    x = torch.randn(256, K).bfloat16()
+    from apex_studio_b200 import ops
+    report = {}
+    for name, rel_delta in (("tiny", 2.0 ** -9), ("small", 2.0 ** -5)):
+        A, B = torch.randn(r, K) * 0.05, torch.randn(N, r) * 0.05
+        delta = B @ A
+        s = rel_delta * W.float().norm() / delta.norm()
+        exact_contrib = x.float() @ (s * delta).t()
+        w_eff = W.to(DEV).clone()
+        ops.linear((B * s).bfloat16().to(DEV).contiguous(), A.bfloat16().t().contiguous().to(DEV), None, epilogue=ops.EPI_GATE_RES,
+                   out=w_eff, gate=None)
+        y_merged = x.float() @ w_eff.float().cpu().t()
+        y_base = x.float() @ W.float().t()
+        # PEFT runtime form in bf16 (each op rounds)
+        xa = torch.nn.functional.linear(x, A.bfloat16())
+        y_rt = (torch.nn.functional.linear(x, W) + torch.nn.functional.linear(xa, B.bfloat16()) * s.bfloat16()).float()
+        exact = y_base + exact_contrib
+        report[name] = dict(contrib_err_merged=rel_l2(y_merged - y_base, exact_contrib), contrib_err_runtime=rel_l2(y_rt - y_base, exact_contrib),
+                            out_err_merged=rel_l2(y_merged, exact), out_err_runtime=rel_l2(y_rt, exact))
+    print("[lora merged vs runtime]", report)
+    assert report["tiny"]["contrib_err_merged"] <= 0.7 and report["small"]["contrib_err_merged"] <= 0.06, report
+    for v in report.values():
+        assert v["contrib_err_merged"] <= v["contrib_err_runtime"] and v["out_err_merged"] <= v["out_err_runtime"], report
+        assert v["out_err_merged"] <= 2.5e-3, report
