@@ -674,20 +674,18 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     pipe_mode = ev ? (ev[0] == '0' ? 0 : 1) : 1;
   }
   const bool use_pair = pipe_mode == 1 && (pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && Sq > 2 * BQ));
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B200_ERR_LAUNCH;
-  static bool attr_done[64] = {};
-  if (!attr_done[dev]) {
-    bool ok = true;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
-    if (!ok) return B200_ERR_LAUNCH;
-    attr_done[dev] = true;
-  }
+  static std::atomic<bool> attr_done[kMaxDevices];
+  if (!once_per_device(attr_done, [] {
+        bool ok = true;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+        return ok;
+      }))
+    return B200_ERR_LAUNCH;
 
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t box[4] = {64, 128, 1, 1};

@@ -316,12 +316,11 @@ int launch(const void* x, const void* wt, Params& p, cudaStream_t st) {
     int rc = make_tmap_bf16_sw(&tmW, wt, 2, dims, str, box, BK == 32);
     if (rc) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(conv3d_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static std::atomic<bool> attr_done[kMaxDevices];   // one array per BK instantiation
+  if (!once_per_device(attr_done, [] {
+        return cudaFuncSetAttribute(conv3d_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess;
+      }))
+    return B200_ERR_LAUNCH;
   const int total = p.T * p.tiles_h * p.tiles_w * p.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
   conv3d_kernel<BK><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(tmX, tmW, p);

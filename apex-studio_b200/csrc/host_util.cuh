@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/apex_b200.h"
 
 namespace b200 {
@@ -57,13 +59,37 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
   return B200_OK;
 }
 
+constexpr int kMaxDevices = 64;
+
+// Index of the current device, or -1.  One-time per-DEVICE setup (the opt-in to large dynamic shared memory is a per-device
+// function attribute; the SM count may differ) is keyed by it; std::atomic keeps concurrent first calls (ctypes releases the
+// GIL) benign -- both threads would do the same idempotent work.
+inline int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
 inline int num_sms() {
-  static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v) return v;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  n[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+
+// Runs `setup()` (returns true on success) once per device; false if it failed or there is no current device.
+template <typename F>
+inline bool once_per_device(std::atomic<bool> (&done)[kMaxDevices], F&& setup) {
+  const int dev = current_device();
+  if (dev < 0) return false;
+  if (done[dev].load(std::memory_order_acquire)) return true;
+  if (!setup()) return false;
+  done[dev].store(true, std::memory_order_release);
+  return true;
 }
 
 #define B200_CHECK_LAUNCH()                                                     \

@@ -405,16 +405,13 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   const int total = p.tiles_m * p.tiles_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(linear_kernel<1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_LAUNCH;
-    if (cudaFuncSetAttribute(linear_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1, 64>::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_LAUNCH;
-    if (cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) != cudaSuccess)
-      return B200_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static std::atomic<bool> attr_done[kMaxDevices];
+  if (!once_per_device(attr_done, [] {
+        return cudaFuncSetAttribute(linear_kernel<1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(linear_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1, 64>::SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+      }))
+    return B200_ERR_LAUNCH;
   if (use_pair) {
     int pairs_avail = num_sms() / 2;
     if (const char* ev = getenv("B200_LINEAR_PAIRS")) pairs_avail = atoi(ev) > 0 ? atoi(ev) : pairs_avail;   // experiments

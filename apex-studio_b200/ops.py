@@ -36,6 +36,14 @@ def _require_cuda_bf16(name: str, t: torch.Tensor) -> None:
         raise ValueError(f"{name} must be bfloat16, got {t.dtype}")
 
 
+def _on_current_device(t: torch.Tensor) -> None:
+    """Kernels are launched on the CURRENT device's current stream; a tensor that lives on another GPU would be
+    dereferenced from the wrong context.  Fail loudly instead (callers use ``torch.cuda.device(t.device)``)."""
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "wrap the call in torch.cuda.device(tensor.device)")
+
+
 def _count(n: int = 1) -> None:
     global launch_count
     launch_count += n
@@ -55,6 +63,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: 
         _require_cuda_bf16(name, t)
         if t.dim() != 4:
             raise ValueError(f"{name} must be [B,H,S,D], got shape {tuple(t.shape)}")
+    _on_current_device(q)
     B, H, Sq, D = q.shape
     Bk, Hk, Sk, Dk = k.shape
     if v.shape != k.shape or Bk != B or Hk != H or Dk != D:
@@ -71,6 +80,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: 
     q, k, v = norm(q), norm(k), norm(v)
     if out is None:
         out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device).transpose(1, 2)
+    else:
+        # the kernel stores 16-byte vectors along the head dim: a wrong-shaped / transposed `out` would corrupt memory
+        _require_cuda_bf16("out", out)
+        if out.device != q.device or tuple(out.shape) != (B, H, Sq, D) or out.stride(3) != 1:
+            raise ValueError(f"out must be a bf16 [B,H,Sq,D] = {(B, H, Sq, D)} tensor on {q.device} with a contiguous last dim, "
+                             f"got shape {tuple(out.shape)}, strides {out.stride()}, device {out.device}")
+        if any(st % 8 for st in out.stride()[:3]) or out.data_ptr() % 16:
+            raise ValueError("out needs 16-byte aligned strides and base address")
     scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
     lib = _lib.load()
     rc = lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Sk, D,
@@ -95,6 +112,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     """
     _require_cuda_bf16("x", x)
     _require_cuda_bf16("weight", weight)
+    _on_current_device(x)
     K = x.shape[-1]
     N = weight.shape[0]
     if weight.dim() != 2 or weight.shape[1] != K:
@@ -219,10 +237,15 @@ def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_peers
     buffers (heads -> tokens exchange fused into the attention epilogue)."""
     for name, t in (("q", q), ("k", k), ("v", v)):
         _require_cuda_bf16(name, t)
+        if t.dim() != 4 or t.stride(3) != 1 or any(st % 8 for st in t.stride()[:3]) or t.data_ptr() % 16:
+            raise ValueError(f"{name} must be [1,H,S,128] with a contiguous last dim and 16-byte aligned strides / base")
+    _on_current_device(q)
     B, H, Sq, D = q.shape
     Sk = k.shape[2]
     if B != 1 or D != 128:
         raise ValueError("attention_scatter needs batch 1 and head_dim 128")
+    if tuple(k.shape) != (1, H, Sk, D) or v.shape != k.shape:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}")
     scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
     lib = _lib.load()
     rc = lib.b200_attn_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), H, Sq, Sk, D, q.stride(1), q.stride(2),

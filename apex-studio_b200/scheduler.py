@@ -30,6 +30,18 @@ import numpy as np
 import torch
 
 
+class SchedulerOutput(tuple):
+    """What ``step(..., return_dict=True)`` returns: diffusers' ``SchedulerOutput`` exposes ``.prev_sample`` and, like every
+    ``BaseOutput``, positional indexing (``out[0]``)."""
+
+    def __new__(cls, prev_sample):
+        return super().__new__(cls, (prev_sample,))
+
+    @property
+    def prev_sample(self):
+        return self[0]
+
+
 class UniPCMultistepScheduler:
     order = 1
 
@@ -195,7 +207,9 @@ class UniPCMultistepScheduler:
         return sample - (1 - sigma_t) * model_output
 
     def step(self, model_output: torch.Tensor, timestep: Union[int, torch.Tensor], sample: torch.Tensor,
-             return_dict: bool = False, generator=None):
+             return_dict: bool = True, generator=None):
+        """unipc.py:651-737; ``return_dict`` defaults to True like the reference (a ``SchedulerOutput`` with ``.prev_sample``,
+        also indexable); the engine passes ``return_dict=False`` and takes ``[0]`` (engine/wan/shared/__init__.py:569)."""
         if self.num_inference_steps is None:
             raise ValueError(
                 "Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
@@ -218,7 +232,7 @@ class UniPCMultistepScheduler:
             self.lower_order_nums += 1
         self._step_index += 1
         if return_dict:
-            return {"prev_sample": prev}
+            return SchedulerOutput(prev)
         return (prev,)
 
     def scale_model_input(self, sample: torch.Tensor, *args, **kwargs) -> torch.Tensor:
@@ -298,16 +312,29 @@ class FlowMatchEulerDiscreteScheduler:
         self._step_index = None
         return self.timesteps
 
-    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = False, **unused):
+    def index_for_timestep(self, timestep, schedule_timesteps: Optional[torch.Tensor] = None) -> int:
+        """upstream ``FlowMatchEulerDiscreteScheduler.index_for_timestep``: equality lookup, SECOND match when duplicated."""
+        ts = self.timesteps if schedule_timesteps is None else schedule_timesteps
+        if isinstance(timestep, torch.Tensor):
+            timestep = timestep.to(ts.device)
+        hits = (ts == timestep).nonzero()
+        if len(hits) == 0:
+            raise ValueError(f"timestep {timestep} is not in the schedule")
+        return hits[1 if len(hits) > 1 else 0].item()
+
+    def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True, **unused):
         if self._step_index is None:
-            self._step_index = self._begin_index or 0
+            # upstream ``_init_step_index``: a strength- / img2img-truncated schedule without set_begin_index starts at the
+            # position of ITS first timestep, not at sigma[0]
+            self._step_index = self.index_for_timestep(timestep) if self._begin_index is None else self._begin_index
         i = self._step_index
         # upstream: ``dt = sigma_next - sigma`` (0-dim fp32 tensors); ``sample.float() + dt * model_output`` -- with a
         # bf16 model_output torch's type promotion makes the product a bf16 op (0-dim operands do not promote)
         dt = self.sigmas[i + 1] - self.sigmas[i]
         prev = sample.to(torch.float32) + dt * model_output
         self._step_index += 1
-        return (prev.to(model_output.dtype),)
+        prev = prev.to(model_output.dtype)
+        return SchedulerOutput(prev) if return_dict else (prev,)
 
 
 def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,

@@ -151,3 +151,31 @@ def test_preview_renderer_follows_the_reference_render_condition():
     with pytest.raises(ValueError):
         denoise.moe_denoise(timesteps=torch.arange(2), latents=torch.ones(1, 4, 1, 2, 2), scheduler=Sch(), high_noise_transformer=fake,
                             use_cfg_guidance=False, render_on_step=True, render_on_step_callback=frames.append)
+
+
+def test_step_returns_scheduler_output_by_default_and_euler_starts_at_its_timestep():
+    """(1) ``step`` defaults to return_dict=True and returns an object with ``.prev_sample`` (reference
+    scheduler/unipc.py:651-737) that is also indexable; (2) FlowMatchEuler without ``set_begin_index`` starts at the index
+    of the timestep it is given (upstream ``_init_step_index``), e.g. on a strength-truncated schedule."""
+    from apex_studio_b200.scheduler import FlowMatchEulerDiscreteScheduler, SchedulerOutput, UniPCMultistepScheduler
+
+    s = UniPCMultistepScheduler(shift=3.0)
+    s.set_timesteps(4)
+    x = torch.randn(1, 4, 2, 2, 2)
+    out = s.step(torch.zeros_like(x), s.timesteps[0], x)
+    assert isinstance(out, SchedulerOutput) and torch.equal(out.prev_sample, out[0])
+    s2 = UniPCMultistepScheduler(shift=3.0)
+    s2.set_timesteps(4)
+    assert isinstance(s2.step(torch.zeros_like(x), s2.timesteps[0], x, return_dict=False), tuple)
+
+    e = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    e.set_timesteps(10)
+    mo = torch.ones_like(x)
+    start = 4                                        # img2img: run only timesteps[4:]
+    got = e.step(mo, e.timesteps[start], x).prev_sample
+    want = x + (e.sigmas[start + 1] - e.sigmas[start]) * mo
+    assert torch.allclose(got, want) and e._step_index == start + 1
+    e2 = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    e2.set_timesteps(10)
+    e2.set_begin_index(2)
+    assert torch.allclose(e2.step(mo, e2.timesteps[2], x)[0], x + (e2.sigmas[3] - e2.sigmas[2]) * mo)
