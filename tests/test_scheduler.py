@@ -168,14 +168,14 @@ def test_step_returns_scheduler_output_by_default_and_euler_starts_at_its_timest
     s2.set_timesteps(4)
     assert isinstance(s2.step(torch.zeros_like(x), s2.timesteps[0], x, return_dict=False), tuple)
 
-    e = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    e = FlowMatchEulerDiscreteScheduler(shift=3.0, use_dynamic_shifting=False)
     e.set_timesteps(10)
     mo = torch.ones_like(x)
     start = 4                                        # img2img: run only timesteps[4:]
     got = e.step(mo, e.timesteps[start], x).prev_sample
     want = x + (e.sigmas[start + 1] - e.sigmas[start]) * mo
     assert torch.allclose(got, want) and e._step_index == start + 1
-    e2 = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    e2 = FlowMatchEulerDiscreteScheduler(shift=3.0, use_dynamic_shifting=False)
     e2.set_timesteps(10)
     e2.set_begin_index(2)
     assert torch.allclose(e2.step(mo, e2.timesteps[2], x)[0], x + (e2.sigmas[3] - e2.sigmas[2]) * mo)
