@@ -402,6 +402,21 @@ def run_b200_arm(args):
         "vae_decode": vae_info,
         "frames_per_sec": (81.0 / (50 * ms_step * 1e-3 + vae_info["ms"] * 1e-3)) if (vae_info and "ms" in vae_info) else None,
     }
+    if world == 1 and not args.no_reference_gpu:
+        # "reference on 1 x B200" (BASELINE.md section 4): the reference's OWN WanTransformerBlock (unmodified files under
+        # baseline/_ref; torch SDPA / flash-attn + cuBLAS + ATen) at the same shape, in a separate process, OUTSIDE every timed
+        # region of this arm.  Reported, extrapolated per step (x 40 layers x 2 forwards), never mixed into `value`.
+        try:
+            torch.cuda.empty_cache()
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_gpu_block.py"), "--iters", "3"],
+                               capture_output=True, text=True, timeout=600)
+            rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            line["reference_gpu"] = json.loads(rows[-1]) if rows else {"error": (r.stderr or r.stdout)[-300:]}
+            rg = line["reference_gpu"]
+            if "steps_per_sec_extrapolated" in rg:
+                rg["this_repo_over_reference_gpu"] = line["value"] / rg["steps_per_sec_extrapolated"]
+        except Exception as e:
+            line["reference_gpu"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_reference_sample(n_tok=2048, repeats=2)
@@ -436,6 +451,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -15,7 +15,8 @@ import sys
 import tempfile
 import types
 
-REFERENCE_API = "/root/reference/apps/api"
+# APEX_REFERENCE_API: an alternative location of the same unmodified files (baseline/_ref/apps/api on the GPU box)
+REFERENCE_API = os.environ.get("APEX_REFERENCE_API") or "/root/reference/apps/api"
 
 
 def available() -> bool:
