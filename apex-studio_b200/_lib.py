@@ -24,6 +24,7 @@ SIGNATURES = {
     "b200_linear": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
     "b200_layernorm_modulate": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i64, _i64, _f, _p]),
     "b200_rmsnorm_rope": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p]),
+    "b200_rmsnorm_rope_batched": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _i, _i64, _i64, _p]),
     "b200_gate_residual": (_i, [_p, _p, _p, _i, _i, _i64, _i64, _p]),
     "b200_cfg_combine": (_i, [_p, _p, _p, _f, _i64, _p]),
     "b200_rmsnorm_rope_scatter": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _i, _i64, _i, _p]),

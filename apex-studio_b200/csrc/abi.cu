@@ -35,6 +35,9 @@ extern "C" int b200_qkv_rmsnorm_rope(const void* x, const void* w_qkv, const voi
                        stream);
   if (rc) return rc;
   char* base = static_cast<char*>(qkv);
+  // q and k in ONE launch when their norm weights are stacked ([2, dim] contiguous, as the model stores them)
+  if (wq_norm && wk_norm && static_cast<const char*>(wk_norm) == static_cast<const char*>(wq_norm) + 2 * (int64_t)dim)
+    return b200_rmsnorm_rope_batched(base, wq_norm, rope, rows, heads, dim / heads, 3 * (int64_t)dim, eps, 2, dim, dim, stream);
   rc = b200_rmsnorm_rope(base, wq_norm, rope, rows, heads, dim / heads, 3 * (int64_t)dim, eps, stream);
   if (rc) return rc;
   return b200_rmsnorm_rope(base + 2 * (int64_t)dim, wk_norm, rope, rows, heads, dim / heads, 3 * (int64_t)dim, eps,

@@ -142,15 +142,20 @@ struct PeerScatter {
   int width;          // channels per peer = (heads / P) * head_dim
   int row0;           // first global token of this rank's shard
   int64_t elem_off;   // element offset of the q / k / v plane inside each peer's receive buffer
+  int64_t batch_elem_off;  // added per batch index (blockIdx.y): the next plane
 };
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                     const __nv_bfloat16* __restrict__ rope, int dim, int head_dim, int64_t ldx, float eps,
-                    const PeerScatter sc) {
+                    const PeerScatter sc, int64_t x_batch_stride, int64_t w_batch_stride) {
   __shared__ float red[THREADS / 32];
   const int64_t row = blockIdx.x;
+  // batch index (grid.y): another column block of the same rows with its own weight vector -- q and k of the fused q|k|v
+  // buffer in ONE launch, or the K blocks of all layers' cross-attention projections
+  x += static_cast<int64_t>(blockIdx.y) * x_batch_stride;
+  if (w != nullptr) w += static_cast<int64_t>(blockIdx.y) * w_batch_stride;
   uint4* xr = reinterpret_cast<uint4*>(x + row * ldx);
   const int nchunks = dim >> 3;
   const int chunks_per_head = head_dim >> 3;
@@ -208,7 +213,7 @@ rmsnorm_rope_kernel(__nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
       } else {
         const int ch = c << 3;
         const int d = ch / sc.width;
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sc.peer[d]) + sc.elem_off +
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(sc.peer[d]) + sc.elem_off + blockIdx.y * sc.batch_elem_off +
                              (static_cast<int64_t>(sc.row0) + row) * sc.width + (ch - d * sc.width);
         *reinterpret_cast<uint4*>(dst) = pack8(f);
       }
@@ -320,17 +325,19 @@ extern "C" int b200_adaln_zero_modulate(const void* x, void* y, const void* scal
 }
 
 static int rmsnorm_rope_launch(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
-                               int64_t ldx, float eps, const PeerScatter& sc, void* stream) {
+                               int64_t ldx, float eps, const PeerScatter& sc, void* stream, int n_batch = 1,
+                               int64_t x_batch_stride = 0, int64_t w_batch_stride = 0) {
   if (!x) return B200_ERR_ARG;
-  if (rows <= 0 || heads <= 0 || head_dim <= 0) return B200_ERR_SHAPE;
-  if ((head_dim % 8) || (ldx % 8)) return B200_ERR_ALIGN;
+  if (rows <= 0 || heads <= 0 || head_dim <= 0 || n_batch <= 0 || n_batch > 65535) return B200_ERR_SHAPE;
+  if ((head_dim % 8) || (ldx % 8) || (x_batch_stride % 8) || (w_batch_stride % 8)) return B200_ERR_ALIGN;
   if (!aligned16(x) || !aligned16(w) || !aligned16(rope)) return B200_ERR_ALIGN;
   const int dim = heads * head_dim;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = dispatch_threads(dim / 8, [&](auto T) {
     constexpr int THREADS = decltype(T)::value;
-    rmsnorm_rope_kernel<THREADS><<<rows, THREADS, 0, st>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                           (const __nv_bfloat16*)rope, dim, head_dim, ldx, eps, sc);
+    rmsnorm_rope_kernel<THREADS><<<dim3(rows, n_batch), THREADS, 0, st>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                                          (const __nv_bfloat16*)rope, dim, head_dim, ldx, eps, sc,
+                                                                          x_batch_stride, w_batch_stride);
     return B200_OK;
   });
   if (rc) return rc;
@@ -342,7 +349,17 @@ extern "C" int b200_rmsnorm_rope(void* x, const void* w, const void* rope, int r
                                  int64_t ldx, float eps, void* stream) {
   PeerScatter sc;
   sc.n_peers = 0;
+  sc.batch_elem_off = 0;
   return rmsnorm_rope_launch(x, w, rope, rows, heads, head_dim, ldx, eps, sc, stream);
+}
+
+extern "C" int b200_rmsnorm_rope_batched(void* x, const void* w, const void* rope, int rows, int heads, int head_dim,
+                                         int64_t ldx, float eps, int n_batch, int64_t x_batch_stride, int64_t w_batch_stride,
+                                         void* stream) {
+  PeerScatter sc;
+  sc.n_peers = 0;
+  sc.batch_elem_off = 0;
+  return rmsnorm_rope_launch(x, w, rope, rows, heads, head_dim, ldx, eps, sc, stream, n_batch, x_batch_stride, w_batch_stride);
 }
 
 extern "C" int b200_rmsnorm_rope_scatter(const void* x, const void* w, const void* rope, int rows, int heads,
@@ -358,6 +375,7 @@ extern "C" int b200_rmsnorm_rope_scatter(const void* x, const void* w, const voi
   sc.width = (heads / n_peers) * head_dim;
   sc.row0 = row0;
   sc.elem_off = dst_elem_offset;
+  sc.batch_elem_off = 0;
   if (dst_elem_offset % 8) return B200_ERR_ALIGN;
   return rmsnorm_rope_launch(const_cast<void*>(x), w, rope, rows, heads, head_dim, ldx, eps, sc, stream);
 }

@@ -8,6 +8,9 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/apex_b200.h"
 
@@ -31,34 +34,6 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // bf16 tensor map with 128-byte swizzle. dims/strides are innermost-first; strides in ELEMENTS for
 // dims 1..rank-1 (dim 0 is contiguous). box is innermost-first. Returns B200_OK or an error code.
-inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_elems, const uint32_t* box) {
-  PFN_encodeTiled enc = get_encode_tiled();
-  if (!enc) return B200_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200_ERR_ALIGN;
-  cuuint64_t gdim[5];
-  cuuint64_t gstr[4];
-  cuuint32_t bx[5];
-  cuuint32_t estr[5];
-  for (int i = 0; i < rank; ++i) {
-    gdim[i] = dims[i];
-    bx[i] = box[i];
-    estr[i] = 1;
-    if (i > 0) {
-      gstr[i - 1] = strides_elems[i] * 2;  // bytes
-      if (gstr[i - 1] % 16 != 0) return B200_ERR_ALIGN;
-    }
-  }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    fprintf(stderr, "[apex_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
-    return B200_ERR_TMAP;
-  }
-  return B200_OK;
-}
-
 constexpr int kMaxDevices = 64;
 
 // Index of the current device, or -1.  One-time per-DEVICE setup (the opt-in to large dynamic shared memory is a per-device
@@ -90,6 +65,91 @@ inline bool once_per_device(std::atomic<bool> (&done)[kMaxDevices], F&& setup) {
   if (!setup()) return false;
   done[dev].store(true, std::memory_order_release);
   return true;
+}
+
+// Descriptor cache: the same (pointer, shape, strides, box, swizzle) recurs on every layer and every step -- weights are
+// resident and the activation workspaces are reused -- so cuTensorMapEncodeTiled (a driver call) runs once per distinct
+// operand instead of 2-3 times per launch.  Direct-mapped, 4096 entries, per-entry sequence lock-free enough for the one
+// issuing thread per device the reference's process model has (ray_tasks.py:181-194); a mutex covers concurrent callers.
+struct TmapKey {
+  uint64_t base, dims[5], strides[4];
+  uint32_t box[5], rank, swizzle, dev;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+inline bool tmap_cache_lookup(const TmapKey& k, CUtensorMap* out, bool store) {
+  static TmapEntry* table = static_cast<TmapEntry*>(calloc(4096, sizeof(TmapEntry)));
+  static std::mutex mu;
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  for (size_t i = 0; i < sizeof(TmapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+  TmapEntry& e = table[(h >> 7) & 4095];
+  std::lock_guard<std::mutex> g(mu);
+  if (store) {
+    e.key = k;
+    e.map = *out;
+    e.valid = true;
+    return true;
+  }
+  if (e.valid && e.key == k) {
+    *out = e.map;
+    return true;
+  }
+  return false;
+}
+
+inline int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_elems, const uint32_t* box);
+
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_elems, const uint32_t* box) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = reinterpret_cast<uint64_t>(base);
+  key.rank = static_cast<uint32_t>(rank);
+  key.swizzle = 128;
+  key.dev = static_cast<uint32_t>(current_device() + 1);
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) key.strides[i - 1] = strides_elems[i];
+  }
+  if (tmap_cache_lookup(key, out, false)) return B200_OK;
+  const int rc = make_tmap_bf16_uncached(out, base, rank, dims, strides_elems, box);
+  if (rc == B200_OK) tmap_cache_lookup(key, out, true);
+  return rc;
+}
+
+inline int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_elems, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return B200_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200_ERR_ALIGN;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_elems[i] * 2;  // bytes
+      if (gstr[i - 1] % 16 != 0) return B200_ERR_ALIGN;
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[apex_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return B200_ERR_TMAP;
+  }
+  return B200_OK;
 }
 
 #define B200_CHECK_LAUNCH()                                                     \

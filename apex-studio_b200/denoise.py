@@ -143,14 +143,19 @@ def moe_denoise(*, timesteps: torch.Tensor, latents: torch.Tensor, scheduler, hi
         if preview_decode_fn is None:
             raise ValueError("render_on_step needs `preview_decode_fn` (e.g. denoise.wan_preview_decode_fn(vae))")
         preview = PreviewRenderer(preview_decode_fn, render_on_step_callback, render_on_step_interval)
+    # host copy of the schedule, ONE device read per run: the expert switch `t >= boundary` and the guidance choice are host
+    # decisions (the reference's `t >= boundary` on a device tensor synchronises every step, :335-337), which also keeps
+    # the per-step path free of host<->device syncs (CUDA-graph friendly)
+    ts_host = timesteps.tolist() if isinstance(timesteps, torch.Tensor) else [float(x) for x in timesteps]
     for i, t in enumerate(timesteps):
         latent_model_input = latents.to(transformer_dtype)
         timestep = t.expand(latents.shape[0])
-        high = select_expert_is_high(t, boundary_timestep)
+        t_host = ts_host[i]
+        high = select_expert_is_high(t_host, boundary_timestep)
         transformer = high_noise_transformer if (high or low_noise_transformer is None) else low_noise_transformer
-        g = select_guidance_scale(t, boundary_timestep, guidance_scale)
+        g = select_guidance_scale(t_host, boundary_timestep, guidance_scale)
         if trace is not None:
-            trace.timesteps.append(int(t))
+            trace.timesteps.append(int(t_host))
             trace.expert.append("high" if (high or low_noise_transformer is None) else "low")
             trace.guidance.append(g)
 

@@ -216,6 +216,33 @@ def rmsnorm_rope_(x: torch.Tensor, weight: Optional[torch.Tensor], rope: Optiona
     return x
 
 
+def rmsnorm_rope_batched_(x: torch.Tensor, weight: torch.Tensor, rope: Optional[torch.Tensor], heads: int, eps: float,
+                          n_batch: int, x_batch_stride: int) -> torch.Tensor:
+    """rmsnorm_rope_ over ``n_batch`` column blocks of the same rows in ONE launch: block b = x[:, b * x_batch_stride :
+    b * x_batch_stride + dim] normalised with weight[b] (weight [n_batch, dim] contiguous).  ``x`` is the FIRST block
+    (a [rows, dim] view); the caller guarantees the other blocks exist behind it in the same rows."""
+    _require_cuda_bf16("x", x)
+    _require_cuda_bf16("weight", weight)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [rows, dim] with a contiguous last dim")
+    rows, dim = x.shape
+    if dim % heads or tuple(weight.shape) != (n_batch, dim) or not weight.is_contiguous():
+        raise ValueError(f"weight must be a contiguous [{n_batch}, {dim}] tensor and dim divisible by heads")
+    if (n_batch - 1) * x_batch_stride + dim > x.stride(0):
+        raise ValueError("the column blocks do not fit into one row of the underlying buffer")
+    head_dim = dim // heads
+    if rope is not None:
+        _require_cuda_bf16("rope", rope)
+        if tuple(rope.shape) != (rows, head_dim) or not rope.is_contiguous():
+            raise ValueError(f"rope must be contiguous [{rows}, {head_dim}], got {tuple(rope.shape)}")
+    lib = _lib.load()
+    rc = lib.b200_rmsnorm_rope_batched(x.data_ptr(), weight.data_ptr(), _ptr(rope), rows, heads, head_dim, x.stride(0), float(eps),
+                                       n_batch, x_batch_stride, dim, _stream())
+    _lib.check(rc, "b200_rmsnorm_rope_batched")
+    _count()
+    return x
+
+
 def rmsnorm_rope_scatter(x: torch.Tensor, weight: Optional[torch.Tensor], rope: Optional[torch.Tensor], heads: int,
                          eps: float, peers, n_peers: int, dst_elem_offset: int, row0: int, *, norm: bool = True) -> None:
     """rmsnorm_rope_ whose result is stored into the peer GPUs' receive planes (tokens -> heads exchange fused into
@@ -408,7 +435,8 @@ def qkv_rmsnorm_rope(x: torch.Tensor, w_qkv: torch.Tensor, b_qkv: Optional[torch
     rc = lib.b200_qkv_rmsnorm_rope(x.data_ptr(), w_qkv.data_ptr(), _ptr(b_qkv), wq_norm.data_ptr(), wk_norm.data_ptr(),
                                    _ptr(rope), out.data_ptr(), rows, dim, heads, x.stride(0), float(eps), _stream())
     _lib.check(rc, "b200_qkv_rmsnorm_rope")
-    _count(3)
+    stacked = wk_norm.data_ptr() == wq_norm.data_ptr() + 2 * dim      # [2, dim] norm weights -> q and k share one launch
+    _count(2 if stacked else 3)
     return out
 
 

@@ -8,13 +8,16 @@ engine's denoise loop (engine/wan/shared/__init__.py:548-563) can call it unchan
 ``TRANSFORMERS_REGISTRY["wan.b200"]`` (INTEGRATION.md).
 
 What runs where: every FLOP of the 40 blocks, the embedders, the patch embedding and the output head goes
-through libapex_b200.so (``ops``): 16 kernel launches per block --
+through libapex_b200.so (``ops``): 13 kernel launches per block --
 
-    layernorm_modulate -> linear(QKV fused) -> rmsnorm_rope(q) -> rmsnorm_rope(k) -> attention
+    layernorm_modulate -> linear(QKV fused) -> rmsnorm_rope(q and k, ONE launch) -> attention
       -> linear(to_out, epilogue h += gate * y)
-    layernorm(affine)  -> linear(q) -> rmsnorm(q) -> linear(KV fused, text) -> rmsnorm(k) -> attention
-      -> linear(to_out, epilogue h += y)
+    layernorm(affine)  -> linear(q) -> rmsnorm(q) -> attention -> linear(to_out, epilogue h += y)
     layernorm_modulate -> linear(ffn.0, epilogue gelu-tanh) -> linear(ffn.2, epilogue h += gate * y)
+
+plus TWO launches per forward for the text side of every layer's cross-attention: the to_k|to_v projections of all layers
+are one GEMM over the stacked weights ([L_text, 5120] x [5120, layers * 10240]) and the norm_k of all layers one batched
+row kernel (they depend on the text context only; the reference recomputes them inside each block, attention.py:345-352).
 
 torch is used for device buffers and for O(dim) glue (the [B,6,dim] modulation table add, SiLU on the
 [B,dim] time embedding, patchify / unpatchify reshapes).  Activations live in preallocated workspaces that
@@ -68,7 +71,7 @@ class _Workspace:
         self.qkv = torch.empty(tokens, 3 * d, dtype=bf, device=device)
         self.attn = torch.empty(tokens, d, dtype=bf, device=device)
         self.ffn = torch.empty(tokens, cfg.ffn_dim, dtype=bf, device=device)
-        self.kv_ctx = torch.empty(ctx_tokens, 2 * d, dtype=bf, device=device)
+        self.kv_ctx = torch.empty(ctx_tokens, cfg.num_layers * 2 * d, dtype=bf, device=device)   # K|V of EVERY layer's cross-attention
 
 
 class WanTransformer3DModel(LoraHostMixin):
@@ -86,6 +89,8 @@ class WanTransformer3DModel(LoraHostMixin):
         self._ws: Optional[_Workspace] = None
         self.dtype = torch.bfloat16
         self.device = None
+        self._use_graph = False
+        self._graphs: Dict[Tuple, object] = {}
 
     # ------------------------------------------------------------------------------------ weights
     @classmethod
@@ -141,7 +146,30 @@ class WanTransformer3DModel(LoraHostMixin):
                                                 dim=0).contiguous()
             w[a2 + ".to_kv.bias"] = torch.cat([w.pop(a2 + ".to_k.bias"), w.pop(a2 + ".to_v.bias")], dim=0).contiguous()
         self.w = w
+        self._stack_shared_layouts()
         return missing, unexpected
+
+    def _stack_shared_layouts(self) -> None:
+        """Storage layouts that let one launch serve several call sites; the per-layer names stay valid as VIEWS (LoRA merges
+        into ``blocks.i.attn2.to_kv`` rows keep working in place):
+          * ``blocks.i.attn1.norm_qk.weight`` [2, dim] = norm_q | norm_k  -> q and k are normalised + rotated in one launch;
+          * ``attn2_kv_all.weight`` [layers * 2 dim, dim] (+ bias) and ``attn2_norm_k_all.weight`` [layers, dim] -> the text side
+            of every layer's cross-attention is one GEMM + one row kernel per forward."""
+        c, w = self.config, self.w
+        L = c.num_layers
+        for i in range(L):
+            a1 = f"blocks.{i}.attn1"
+            qk = torch.stack([w[a1 + ".norm_q.weight"], w[a1 + ".norm_k.weight"]], dim=0).contiguous()
+            w[a1 + ".norm_qk.weight"], w[a1 + ".norm_q.weight"], w[a1 + ".norm_k.weight"] = qk, qk[0], qk[1]
+        kv_w = torch.cat([w[f"blocks.{i}.attn2.to_kv.weight"] for i in range(L)], dim=0).contiguous()
+        kv_b = torch.cat([w[f"blocks.{i}.attn2.to_kv.bias"] for i in range(L)], dim=0).contiguous()
+        nk = torch.stack([w[f"blocks.{i}.attn2.norm_k.weight"] for i in range(L)], dim=0).contiguous()
+        d2 = 2 * c.inner_dim
+        for i in range(L):
+            w[f"blocks.{i}.attn2.to_kv.weight"] = kv_w[i * d2:(i + 1) * d2]
+            w[f"blocks.{i}.attn2.to_kv.bias"] = kv_b[i * d2:(i + 1) * d2]
+            w[f"blocks.{i}.attn2.norm_k.weight"] = nk[i]
+        w["attn2_kv_all.weight"], w["attn2_kv_all.bias"], w["attn2_norm_k_all.weight"] = kv_w, kv_b, nk
 
     def init_random_weights(self, device="cuda", seed: int = 1234, std: float = 0.02):
         """Synthetic weights of the architecture's shapes generated ON the device (bench.py; there are no
@@ -182,6 +210,7 @@ class WanTransformer3DModel(LoraHostMixin):
         w["scale_shift_table"] = rnd(1, 2, d, scale=d ** -0.5)
         lin("proj_out", c.out_channels * pp, d)
         self.w = w
+        self._stack_shared_layouts()
         return self
 
     def lora_target(self, module: str):
@@ -201,7 +230,14 @@ class WanTransformer3DModel(LoraHostMixin):
         raise ValueError(f"Target module {module} not found in the model (or not a linear layer the b200 path adapts)")
 
     def parameter_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self.w.values())
+        """bytes of distinct weight storage (the stacked layouts alias their per-layer views)"""
+        seen, total = set(), 0
+        for t in self.w.values():
+            st = t.untyped_storage()
+            if st.data_ptr() not in seen:
+                seen.add(st.data_ptr())
+                total += st.nbytes()
+        return total
 
     # ------------------------------------------------------------------------------------ pieces
     def _rope(self, grid: Tuple[int, int, int]) -> torch.Tensor:
@@ -301,9 +337,9 @@ class WanTransformer3DModel(LoraHostMixin):
         q2 = ops.linear(xn, w[p + ".attn2.to_q.weight"], w[p + ".attn2.to_q.bias"], out=ws.attn)
         ops.rmsnorm_rope_(q2, w[p + ".attn2.norm_q.weight"], None, heads, eps)
         L = ctx.shape[0]
-        ops.linear(ctx, w[p + ".attn2.to_kv.weight"], w[p + ".attn2.to_kv.bias"], out=ws.kv_ctx)
-        k2, v2 = ws.kv_ctx[:, :d], ws.kv_ctx[:, d:]
-        ops.rmsnorm_rope_(k2, w[p + ".attn2.norm_k.weight"], None, heads, eps)
+        # K | V of this layer's cross-attention: column block i of ws.kv_ctx, projected + normalised for ALL layers by
+        # ``text_kv`` at the top of the forward
+        k2, v2 = ws.kv_ctx[:, i * 2 * d:i * 2 * d + d], ws.kv_ctx[:, i * 2 * d + d:(i + 1) * 2 * d]
         o2 = ws.norm  # norm output is dead once q2 exists
         ops.attention(as4(q2, S), as4(k2, L), as4(v2, L), out=as4(o2, S))
         ops.linear(o2, w[p + ".attn2.to_out.0.weight"], w[p + ".attn2.to_out.0.bias"], epilogue=ops.EPI_GATE_RES,
@@ -314,10 +350,56 @@ class WanTransformer3DModel(LoraHostMixin):
         ops.mlp_gelu_(h, ws.norm, w[p + ".ffn.net.0.proj.weight"], w[p + ".ffn.net.0.proj.bias"],
                       w[p + ".ffn.net.2.weight"], w[p + ".ffn.net.2.bias"], c_gate, ws.ffn)
 
+    def text_kv(self, ctx: torch.Tensor, ws: _Workspace) -> None:
+        """to_k | to_v (attention.py:346-347) and norm_k (:349-352) of EVERY layer's cross-attention on the text context [L, dim]
+        -> ws.kv_ctx [L, layers * 2 dim]: one GEMM over the stacked weights, one batched row kernel."""
+        c, w = self.config, self.w
+        ops.linear(ctx, w["attn2_kv_all.weight"], w["attn2_kv_all.bias"], out=ws.kv_ctx)
+        ops.rmsnorm_rope_batched_(ws.kv_ctx[:, :c.inner_dim], w["attn2_norm_k_all.weight"], None, c.num_attention_heads, c.eps,
+                                  c.num_layers, 2 * c.inner_dim)
+
+    # ------------------------------------------------------------------------------------ CUDA graph
+    def enable_cuda_graph(self, enabled: bool = True) -> None:
+        """Replay the whole forward (13 launches x layers + glue) from ONE CUDA graph per input shape.  Every
+        kernel goes through the C ABI on the current stream with host-built TMA descriptors passed by value, weights and
+        workspaces are static, nothing synchronises with the host -> capture once (after two warm-up runs), replay for every
+        later step, cond and uncond alike (the text embedding is a graph INPUT).  Bit-identical to eager execution
+        (tests/test_gpu_parity.py::test_wan_forward_cuda_graph_replay_is_bit_identical).  Single-GPU forwards only: the
+        sequence-parallel path contains collectives / symmetric-memory barriers and stays eager."""
+        self._use_graph = bool(enabled)
+        if not enabled:
+            self._graphs.clear()
+
+    def _graphed(self, hidden_states: torch.Tensor, timestep: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        from ..graph import GraphedCallable
+
+        key = (tuple(hidden_states.shape), tuple(text.shape), tuple(timestep.shape), str(timestep.dtype))
+        g = self._graphs.get(key)
+        if g is None:
+            g = GraphedCallable(lambda h, t, e: self._forward_eager(h, t, e)[0], [hidden_states, timestep, text])
+            self._graphs[key] = g
+        # the graph's output buffer is static: hand out a copy (the engine keeps `cond` alive across the `uncond` forward)
+        return g(hidden_states, timestep, text).clone()
+
     # ------------------------------------------------------------------------------------ forward
     @torch.inference_mode()
     def forward(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
                 return_dict: bool = False, **unused):
+        """hidden_states [B,C,F,H,W] (bf16), timestep [B] int64, encoder_hidden_states [B,L,text_dim] ->
+        ([B,C_out,F,H,W],); see ``_forward_eager``.  With ``enable_cuda_graph()`` single-GPU forwards replay a captured graph."""
+        par = unused.get("parallel", None)
+        if self._use_graph and (par is None or par.world_size == 1):
+            if not self.w:
+                raise RuntimeError("weights not loaded: call load_state_dict() or init_random_weights()")
+            out = self._graphed(hidden_states.to(device=self.device, dtype=torch.bfloat16).contiguous(),
+                                timestep.to(self.device).contiguous(),
+                                encoder_hidden_states.to(device=self.device, dtype=torch.bfloat16).contiguous())
+            return {"sample": out} if return_dict else (out,)
+        return self._forward_eager(hidden_states, timestep, encoder_hidden_states, return_dict=return_dict, **unused)
+
+    @torch.inference_mode()
+    def _forward_eager(self, hidden_states: torch.Tensor, timestep: torch.Tensor, encoder_hidden_states: torch.Tensor,
+                       return_dict: bool = False, **unused):
         """hidden_states [B,C,F,H,W] (bf16), timestep [B] int64, encoder_hidden_states [B,L,text_dim] ->
         ([B,C_out,F,H,W],).  Batch elements run one after another, exactly like the reference runs cond and
         uncond as two B=1 forwards (engine/wan/shared/__init__.py:548-563)."""
@@ -341,6 +423,7 @@ class WanTransformer3DModel(LoraHostMixin):
         outs = []
         for bi in range(b):
             h = tokens[bi]
+            self.text_kv(ctx[bi], ws)
             for i in range(c.num_layers):
                 self.block(i, h, ctx[bi], temb6[bi], rope, ws, par)
             # output head (model.py:1841-1868): (table + temb) in bf16, modulated norm, proj_out

@@ -202,6 +202,9 @@ def run_b200_arm(args):
     cfg = WanConfig(num_layers=args.layers)
     high = WanTransformer3DModel(cfg).init_random_weights(dev, seed=1234)
     low = WanTransformer3DModel(cfg).init_random_weights(dev, seed=4321)
+    if args.cuda_graph and world == 1:
+        high.enable_cuda_graph()
+        low.enable_cuda_graph()
     sch = UniPCMultistepScheduler(shift=3.0)
     sch.set_timesteps(50, device=dev)
     boundary = 0.875 * sch.num_train_timesteps
@@ -379,7 +382,7 @@ def run_b200_arm(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD if full_model else f"REDUCED ({args.layers} layers, debug only) " + WORKLOAD,
-                   "layers": args.layers, "experts_resident": 2, "guidance_scale": [4.0, 3.0], "flow_shift": 3.0,
+                   "layers": args.layers, "experts_resident": 2, "cuda_graph": bool(args.cuda_graph and world == 1), "guidance_scale": [4.0, 3.0], "flow_shift": 3.0,
                    "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}" + (" (peer-memory fused exchange)" if (
                        par.use_p2p and par.sp_size > 1) else (" (NCCL all-to-all)" if par.sp_size > 1 else "")), "l2": "inputs larger than L2 (0.77 GB activations)",
                    "timesteps_run": f"first {args.warmup + args.steps + e2e_steps} of 50"},
@@ -452,6 +455,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vae", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay each expert's forward from one CUDA graph (N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -121,6 +121,16 @@ int b200_cfg_combine(const void* cond, const void* uncond, void* out, float guid
  * --------------------------------------------------------------------------------------------------------- */
 
 /*
+ * b200_rmsnorm_rope over `n_batch` column blocks of the same rows in ONE launch: block b is x + b * x_batch_stride (elements)
+ * with weight w + b * w_batch_stride; the RoPE table is shared.  Call sites: q and k of the self-attention processor
+ * (attention.py:349-370: norm_q, norm_k, RoPE on both) with n_batch = 2, x_batch_stride = dim inside the fused q|k|v buffer;
+ * norm_k of every layer's cross-attention (attention.py:349-352 on the text context) with n_batch = num_layers over the
+ * [L_text, num_layers * 2 * dim] output of the batched to_k|to_v projection.
+ */
+int b200_rmsnorm_rope_batched(void* x, const void* w, const void* rope, int rows, int heads, int head_dim, int64_t ldx,
+                              float eps, int n_batch, int64_t x_batch_stride, int64_t w_batch_stride, void* stream);
+
+/*
  * b200_rmsnorm_rope with the "tokens -> heads" scatter: channel c of local token r is written to
  *   peers[c / width] + dst_elem_offset + (row0 + r) * width + c % width,   width = (heads / n_peers) * head_dim,
  * i.e. into the [S_total, width] plane (q, k or v -- selected by dst_elem_offset) of the rank that owns that head

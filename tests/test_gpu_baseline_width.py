@@ -79,6 +79,7 @@ def test_wan_block_at_a14b_width_vs_oracle():
     model.load_state_dict(w32, device=DEV)
     h = h0[0].to(DEV).clone()
     ws = _Workspace(S, L, model.config, torch.device(DEV))
+    model.text_kv(ctx[0].to(DEV), ws)            # to_k | to_v + norm_k of the cross-attention, hoisted out of the block
     model.block(0, h, ctx[0].to(DEV), temb6[0].to(DEV), model._rope(grid), ws)
     torch.cuda.synchronize()
 

@@ -280,6 +280,45 @@ def test_dit_forward_vs_reference_golden(name):
     assert rel_l2(out, ref_bf16) <= 2e-2
 
 
+def test_wan_forward_cuda_graph_replay_is_bit_identical():
+    """SURVEY 8 f1 for Wan: the forward captured into ONE CUDA graph replays bit-identically to eager execution, for a second
+    (different) input too, and the whole CFG denoise loop run on graphs equals the eager loop bit for bit."""
+    from apex_studio_b200 import denoise, ops
+    from apex_studio_b200.scheduler import UniPCMultistepScheduler
+
+    cfg = CONFIGS["dit_s72"]
+    model, _ = _build_model(cfg)
+    g = np.load(os.path.join(GOLDEN, "dit_s72.npz"))
+    lat, t, text = torch.from_numpy(g["latents"]), torch.from_numpy(g["timestep"]), torch.from_numpy(g["text"])
+    a = (lat.to(DEV, torch.bfloat16), t.to(DEV), text.to(DEV, torch.bfloat16))
+    b = ((lat * 0.5 + 0.1).to(DEV, torch.bfloat16), (t - 300).to(DEV), (text * -0.7).to(DEV, torch.bfloat16))
+    eager_a, eager_b = model(*a)[0].clone(), model(*b)[0].clone()
+    n0 = ops.launch_count
+    model(*a)
+    per_forward = ops.launch_count - n0
+    L = cfg["num_layers"]
+    assert per_forward == 13 * L + 2 + 8, per_forward        # 13 per block, 2 for all layers' text K|V, 8 embedders / patchify / head
+    model.enable_cuda_graph()
+    ga = model(*a)[0]
+    gb = model(*b)[0]
+    ga2 = model(*a)[0]
+    assert torch.equal(ga, eager_a) and torch.equal(gb, eager_b) and torch.equal(ga2, eager_a)
+    assert len(model._graphs) == 1
+
+    def run(graph):
+        m, _ = _build_model(cfg)
+        if graph:
+            m.enable_cuda_graph()
+        sch = UniPCMultistepScheduler(shift=3.0)
+        sch.set_timesteps(5, device=DEV)
+        return denoise.moe_denoise(timesteps=sch.timesteps, latents=lat.to(DEV), scheduler=sch, high_noise_transformer=m,
+                                   low_noise_transformer=m, boundary_timestep=875.0, guidance_scale=[4.0, 3.0],
+                                   transformer_kwargs=dict(encoder_hidden_states=text.to(DEV, torch.bfloat16)),
+                                   unconditional_transformer_kwargs=dict(encoder_hidden_states=(text * 0).to(DEV, torch.bfloat16)))
+
+    assert torch.equal(run(True), run(False))
+
+
 def test_denoise_loop_small_vs_oracle():
     """6 UniPC steps, CFG on, dual experts, small DiT: integer trace exact, latents close to the oracle loop."""
     from apex_studio_b200 import denoise

@@ -147,8 +147,11 @@ def test_merge_equals_fp32_math_and_unmerge_is_bit_exact(rank):
         # and close to the exact (unrounded factors) merge
         exact = lora_oracle.merged_weight(w32[mod + ".weight"], [(lo[mod + ".lora_A.weight"], lo[mod + ".lora_B.weight"], 0.8)])
         assert rel_l2(got, exact) <= 4e-3
-    untouched = [k for k in base if not any(m.lora_target(mod)[0] == k for mod in MODULES)]
-    assert all(torch.equal(m.w[k], base[k]) for k in untouched)
+    # keys that share no storage with an adapted weight (the stacked layouts alias their per-layer views, e.g.
+    # attn2_kv_all.weight <-> blocks.N.attn2.to_kv.weight)
+    touched = {m.w[m.lora_target(mod)[0]].untyped_storage().data_ptr() for mod in MODULES}
+    untouched = [k for k in base if m.w[k].untyped_storage().data_ptr() not in touched]
+    assert len(untouched) > 10 and all(torch.equal(m.w[k], base[k]) for k in untouched)
     m.set_adapters(["x"], [0.0])
     assert all(torch.equal(m.w[k], base[k]) for k in base)
     m.set_adapters(["x"], [1.0])
