@@ -21,6 +21,15 @@
 namespace b200 {
 namespace linear {
 
+#ifndef LINEAR_PARKED
+#define LINEAR_PARKED 1
+#endif
+// every wait of this kernel is long (a k-block for the producer / issuer, a whole tile for the epilogue warps): park in
+// hardware instead of re-polling (see mbar_wait_parked)
+B200_DEVICE void lin_wait(uint64_t* bar, uint32_t parity) {
+  if (LINEAR_PARKED) mbar_wait_parked(bar, parity); else mbar_wait(bar, parity);
+}
+
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
@@ -54,7 +63,8 @@ struct Params {
   int epi;
   int bias_row;
   int tiles_m, tiles_n;
-  int group_m;   // row-tiles per rasterisation group (the W panel of a group stays in L2)
+  int group_m;   // row-tiles per rasterisation group (the A rows of a group stay in L2 while its n-tiles are swept)
+  int panel_n;   // column-tiles per panel: the W panel (panel_n x BN x K) stays in L2 while ALL row groups sweep it
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -65,23 +75,42 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + fast_tanh(inner));
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
-  const int per_group = group_m * tiles_n;
-  const int group = tile / per_group;
+// Two-level rasterisation for L2 residency (the output is walked panel by panel, inside a panel group by group, inside a group
+// column by column, rows fastest):  W panel (panel_n x BN x K bytes x 2) + A group (group_m x tile rows x K x 2) are sized by the
+// host to fit the 126 MB L2 together, so W is read from HBM once per panel... once in total, and A once per panel.  With one
+// 16-row-tile group over the whole N (round 1) the 75600 x 15360 x 5120 GEMM read 7.8 GB from HBM for 0.93 GB of operands and
+// the N = 5120 shapes ran 25 % faster with group_m = 4 (profiles/r02_gemm_groupm_sweep.log).
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int panel_n, int& tm, int& tn) {
+  const int per_panel = tiles_m * panel_n;
+  const int panel = tile / per_panel;
+  const int first_n = panel * panel_n;
+  const int pw = min(tiles_n - first_n, panel_n);          // width of this panel (the last one may be narrower)
+  const int rp = tile - panel * per_panel;                 // all full panels precede a narrower last one
+  const int per_group = group_m * pw;
+  const int group = rp / per_group;
   const int first_m = group * group_m;
   const int gsz = min(tiles_m - first_m, group_m);
-  const int r = tile - group * per_group;
+  const int r = rp - group * per_group;
   tm = first_m + r % gsz;
-  tn = r / gsz;
+  tn = first_n + r / gsz;
 }
 
-template <int NCTA, int BN_T>
+// QUAD (NCTA = 2 only): clusters of FOUR CTAs = two pairs that own horizontally adjacent 256 x 256 tiles (same rows, columns tn
+// and tn + 1).  Both pairs need the same A rows, so every A box is fetched from L2 ONCE and TMA-multicast into both pairs'
+// shared memory (each CTA issues one 64-row box for itself and its counterpart in the other pair): L2 -> SM traffic per tile and
+// k-block drops from 64 KB to 48 KB.  A slot may only be refilled when BOTH pairs have consumed it: their commits are multicast
+// to all four CTAs and the `empty` barriers count two arrivals.
+template <int NCTA, int BN_T, bool QUAD = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+  static_assert(!QUAD || NCTA == 2, "QUAD is a form of the CTA-pair kernel");
   constexpr int STAGES = Cfg<NCTA, BN_T>::STAGES;
   constexpr int STAGE_BYTES = Cfg<NCTA, BN_T>::STAGE_BYTES;
   constexpr int B_ROWS = Cfg<NCTA, BN_T>::B_ROWS;
-  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the CTA pair
+  constexpr int CLUSTER = QUAD ? 4 : NCTA;
+  const uint32_t cl_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the cluster
+  const uint32_t cta_rank = cl_rank & 1u;                         // rank inside the CTA pair
+  const uint32_t pair_id = cl_rank >> 1;                          // QUAD: which of the two pairs (column tile offset)
   const bool leader = cta_rank == 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,7 +129,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);         // pair: the LEADER's barrier collects the bytes of both CTAs (only the leader arrives)
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], QUAD ? 2 : 1);   // QUAD: both pairs must have consumed the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -123,9 +152,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_kb = (p.K + BK - 1) / BK;
-  const int total_tiles = p.tiles_m * p.tiles_n;      // tiles of (BM * NCTA) x BN
-  const int first_tile = blockIdx.x / NCTA;             // one tile stream per CTA pair
-  const int tile_step = gridDim.x / NCTA;
+  // QUAD: p.tiles_n counts column tile PAIRS; this CTA pair owns column tile 2 * tn + pair_id of each
+  const int total_tiles = p.tiles_m * p.tiles_n;      // tiles of (BM * NCTA) x BN (QUAD: x 2 BN)
+  const int first_tile = blockIdx.x / CLUSTER;          // one tile stream per CTA pair (QUAD: per quad)
+  const int tile_step = gridDim.x / CLUSTER;
+  const uint16_t commit_mask = QUAD ? static_cast<uint16_t>(3u << (2 * pair_id)) : static_cast<uint16_t>(3);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -134,9 +165,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t phase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         int tm, tn;
-        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, p.panel_n, tm, tn);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          lin_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           if constexpr (NCTA == 2) {
@@ -144,10 +175,18 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // arrives: it may only refill a slot after the leader's MMAs of the previous round were committed (its own
             // `empty` barrier, multicast), i.e. after the leader's barrier finished that round -- so its bytes can land
             // before the leader's expect_tx of the same round (the tx-count goes negative transiently, which is legal).
-            const uint32_t lbar = mapa_u32(&full[stage], 0);
+            const uint32_t lbar = leader_bar(&full[stage]);
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-            tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * BM);
-            tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN_T + static_cast<int>(cta_rank) * B_ROWS);
+            if constexpr (QUAD) {
+              // rows [64 * pair_id, +64) of this CTA's 128 A rows, multicast to this CTA and its counterpart in the other pair
+              const uint16_t mc = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2)));
+              tma_load_2d_2sm_mc(sa + pair_id * (A_BYTES / 2), &tmA, lbar, kb * BK,
+                                 (tm * 2 + static_cast<int>(cta_rank)) * BM + static_cast<int>(pair_id) * (BM / 2), mc);
+              tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, (tn * 2 + static_cast<int>(pair_id)) * BN_T + static_cast<int>(cta_rank) * B_ROWS);
+            } else {
+              tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * BM);
+              tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN_T + static_cast<int>(cta_rank) * B_ROWS);
+            }
           } else {
             mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
             tma_load_2d(sa, &tmA, &full[stage], kb * BK, tm * BM);
@@ -170,11 +209,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        lin_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          lin_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
@@ -185,13 +224,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (NCTA == 2) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
+          if constexpr (QUAD) umma_commit_2sm_mask(&empty[stage], 0xF);       // all four CTAs: a slot is shared by both pairs
+          else if constexpr (NCTA == 2) umma_commit_2sm(&empty[stage]);
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if constexpr (NCTA == 2) umma_commit_2sm(&acc_full[acc]); else umma_commit(&acc_full[acc]);
+        if constexpr (NCTA == 2) umma_commit_2sm_mask(&acc_full[acc], commit_mask); else umma_commit(&acc_full[acc]);
       }
     }
   } else {
@@ -200,17 +241,17 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     int it = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       int tm, tn;
-      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, p.panel_n, tm, tn);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&acc_full[acc], acc_phase);
+      lin_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const int row = (tm * NCTA + static_cast<int>(cta_rank)) * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN_T / 32; ++c) {
-        const int col0 = tn * BN_T + c * 32;
+        const int col0 = (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn) * BN_T + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_x32(t_addr + c * 32, r);
@@ -321,7 +362,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (NCTA == 2) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+        if constexpr (NCTA == 2) mbar_arrive_cluster(leader_bar(&acc_empty[acc]));
         else mbar_arrive(&acc_empty[acc]);
       }
     }
@@ -374,12 +415,23 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   if (small_m) use_pair = false;
   const int ncta = use_pair ? 2 : 1;
   const int bn = small_m ? 64 : BN;
+  // QUAD (clusters of 4 = two pairs sharing A through TMA multicast).  A cluster of 4 can only use 132 of the 148 SMs (33 quads
+  // fit: GPC sizes 16 / 18 / 20) yet measures >= the pair form on every big shape under the power cap (Wan qkv +2.5 %, ffn.2
+  // +13 %, profiles/r02_gemm_quad_ab.log): default for problems of >= 1000 pair tiles, where 66 vs 74 tile slots per wave does
+  // not matter.  B200_LINEAR_QUAD=1 / 0 forces / disables it.
+  static int quad_mode = -2;
+  if (quad_mode == -2) {
+    const char* ev = getenv("B200_LINEAR_QUAD");
+    quad_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+  }
+  const int64_t pair_tiles = static_cast<int64_t>((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const bool use_quad = use_pair && ((N + BN - 1) / BN) >= 2 && (quad_mode == 1 || (quad_mode == -1 && pair_tiles >= 1000));
 
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[2] = {1, (uint64_t)lda};
-    uint32_t box[2] = {BK, BM};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(use_quad ? BM / 2 : BM)};
     int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -400,8 +452,24 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.bias_row = bias_row;
   p.tiles_m = (M + BM * ncta - 1) / (BM * ncta);
   p.tiles_n = (N + bn - 1) / bn;
-  p.group_m = GROUP_M;
-  if (const char* ev = getenv("B200_LINEAR_GROUP_M")) p.group_m = atoi(ev) > 0 ? atoi(ev) : GROUP_M;   // experiments
+  if (use_quad) p.tiles_n = (p.tiles_n + 1) / 2;      // column tile PAIRS
+  {
+    // rasterisation sized for L2: ~24 MB of A rows per group (4..16 row tiles), ~64 MB of W per panel (>= 8 column tiles), panels
+    // of equal width (see tile_coords).
+    // Measured effect under the power cap: within +-3 % of the round-1 order on every Wan shape (profiles/r02_gemm_raster_sweep.log)
+    // -- HBM traffic drops 3x but the kernel is bound by energy per FLOP elsewhere.
+    const double row_tile_bytes = 2.0 * BM * ncta * K, col_tile_bytes = 2.0 * bn * (use_quad ? 2 : 1) * K;
+    int gm = static_cast<int>(24.0e6 / row_tile_bytes);
+    int pn = static_cast<int>(64.0e6 / col_tile_bytes);
+    p.group_m = gm < 4 ? 4 : (gm > GROUP_M ? GROUP_M : gm);
+    pn = pn < 8 ? 8 : pn;
+    const int n_panels = (p.tiles_n + pn - 1) / pn;
+    p.panel_n = (p.tiles_n + n_panels - 1) / n_panels;
+    if (const char* ev = getenv("B200_LINEAR_GROUP_M")) p.group_m = atoi(ev) > 0 ? atoi(ev) : p.group_m;   // experiments
+    if (const char* ev = getenv("B200_LINEAR_PANEL_N")) p.panel_n = atoi(ev) > 0 ? atoi(ev) : p.panel_n;
+    if (p.panel_n > p.tiles_n) p.panel_n = p.tiles_n;
+    if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+  }
   const int total = p.tiles_m * p.tiles_n;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -409,10 +477,40 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   if (!once_per_device(attr_done, [] {
         return cudaFuncSetAttribute(linear_kernel<1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess &&
                cudaFuncSetAttribute(linear_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1, 64>::SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+               cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(linear_kernel<2, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
       }))
     return B200_ERR_LAUNCH;
-  if (use_pair) {
+  if (use_quad) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static std::atomic<int> quads_fit[kMaxDevices];
+    const int dev = current_device();
+    int fit = dev >= 0 ? quads_fit[dev].load() : 0;
+    if (fit == 0) {
+      cfg.gridDim = dim3(4 * (num_sms() / 4), 1, 1);
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, linear_kernel<2, BN, true>, &cfg) != cudaSuccess || ncl <= 0) ncl = num_sms() / 4 - 4;
+      fit = ncl;
+      if (dev >= 0) quads_fit[dev].store(fit);
+      if (getenv("B200_LINEAR_DEBUG")) fprintf(stderr, "[apex_b200] linear quad kernel: %d clusters of 4 fit\n", fit);
+    }
+    const int quads = total < fit ? total : fit;
+    cfg.gridDim = dim3(4 * quads, 1, 1);
+    if (cudaLaunchKernelEx(&cfg, linear_kernel<2, BN, true>, tmA, tmB, p) != cudaSuccess) {
+      cudaGetLastError();
+      return B200_ERR_LAUNCH;
+    }
+  } else if (use_pair) {
     int pairs_avail = num_sms() / 2;
     if (const char* ev = getenv("B200_LINEAR_PAIRS")) pairs_avail = atoi(ev) > 0 ? atoi(ev) : pairs_avail;   // experiments
     const int pairs = total < pairs_avail ? total : pairs_avail;

@@ -267,6 +267,18 @@ B200_DEVICE void tma_load_4d_2sm(void* smem, const CUtensorMap* m, uint32_t bar_
 B200_DEVICE void mbar_arrive_release_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// 2-SM TMA load MULTICAST to the CTAs in `mask`: the box lands at the same shared-memory offset in every destination CTA and
+// its bytes complete on the mbarrier at `bar_addr`'s offset in each destination's PAIR LEADER (bar_addr = this CTA's own
+// shared address with the pair bit cleared: leader_bar()).
+B200_DEVICE void tma_load_2d_2sm_mc(void* smem, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// shared::cluster address of `bar` in the even (leader) CTA of this CTA's pair: a CTA's own shared-window addresses carry its
+// rank in the cluster from bit 24 up, clearing bit 24 turns an odd rank into its even partner
+B200_DEVICE uint32_t leader_bar(const void* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }
 B200_DEVICE void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -300,6 +312,11 @@ B200_DEVICE void umma_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, 
       : "memory");
 }
 // Arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once the previously issued MMAs completed
+B200_DEVICE void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
 B200_DEVICE void umma_commit_2sm(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

@@ -52,7 +52,8 @@ def test_attention_form_in_subprocess(env):
     assert len(errs) == 6 and all(v <= 5e-3 for v in errs.values()), errs
 
 
-@pytest.mark.parametrize("env", [{"B200_LINEAR_2CTA": "0"}, {"B200_LINEAR_2CTA": "1"}, {"B200_LINEAR_SMALLM": "1"}])
+@pytest.mark.parametrize("env", [{"B200_LINEAR_2CTA": "0"}, {"B200_LINEAR_2CTA": "1"}, {"B200_LINEAR_SMALLM": "1"},
+                                 {"B200_LINEAR_QUAD": "1"}, {"B200_LINEAR_QUAD": "0"}])
 def test_linear_kernel_forms_in_subprocess(env):
     res = _run([sys.executable, "-c", GEMM_CODE], env)
     assert len(res) == 5 and all(v <= 4e-3 for v in res.values()), (env, res)
