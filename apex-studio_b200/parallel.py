@@ -22,7 +22,7 @@ on the device by the caller.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Tuple
+from typing import Sequence, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -246,6 +246,22 @@ def all_to_all_single(recv: torch.Tensor, send: torch.Tensor, group) -> None:
     chunk = send.shape[0] // P
     for src in range(P):
         recv[src * chunk:(src + 1) * chunk].copy_(parts[src][me * chunk:(me + 1) * chunk])
+
+
+def deal_lpt(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Longest-processing-time-first dealing of items (VAE tiles, cost = latent pixels of the tile) to ranks: items sorted by
+    decreasing cost (ties: by index) go to the currently least-loaded rank (ties: lowest rank).  Deterministic, identical on every
+    rank.  For the 720p Wan latent (28 tiles: 18 full 32 x 32, 10 smaller edge tiles) on 8 ranks the heaviest rank carries 3 full
+    tiles = 7.7 x less than the whole decode, where round-robin gives one rank 4 full tiles (5.8 x).  Returns the sorted item
+    lists per rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    load = [0.0] * world_size
+    mine: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        mine[r].append(i)
+        load[r] += float(costs[i])
+    return [sorted(m) for m in mine]
 
 
 def deal_round_robin(n_items: int, world_size: int, rank: int) -> List[int]:

@@ -32,7 +32,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .. import _lib, ops
-from ..parallel import ParallelContext, deal_round_robin
+from ..parallel import ParallelContext, deal_lpt
 from .wan import AutoencoderKLWan, _stream
 
 
@@ -351,14 +351,15 @@ class AutoencoderKLHunyuanVideo15:
         nrows = len(range(0, H, ov))
         world = par.world_size if par is not None else 1
         rank = par.rank if par is not None else 0
-        mine = deal_round_robin(len(grid), world, rank)
+        owners = deal_lpt([min(tl, H - i) * min(tl, W - j) for i, j in grid], world)     # by cost: edge tiles are smaller
+        mine = owners[rank]
         T_out = 1 + self.temporal_compression_ratio * (T - 1)
         tiles: Dict[int, torch.Tensor] = {}
         for idx in mine:
             i, j = grid[idx]
             tiles[idx] = self.decode_tile(z[:, :, i:i + tl, j:j + tl].contiguous())
         if world > 1:
-            tiles = self._allgather_tiles(tiles, grid, H, W, T_out, par)
+            tiles = self._allgather_tiles(tiles, grid, H, W, T_out, par, owners)
         # output extent: every tile contributes min(limit, its size) pixels (model.py:1113-1117)
         col_w = [min(limit, min(tl, W - j) * r) for j in range(0, W, ov)]
         row_h = [min(limit, min(tl, H - i) * r) for i in range(0, H, ov)]
@@ -375,11 +376,12 @@ class AutoencoderKLHunyuanVideo15:
             y0 += row_h[ri]
         return frame
 
-    def _allgather_tiles(self, tiles, grid, H, W, T_out, par: ParallelContext):
+    def _allgather_tiles(self, tiles, grid, H, W, T_out, par: ParallelContext, owners):
         r = self.spatial_compression_ratio
         th = tw = self.tile_sample_min_height
         tl = self.tile_latent_min_height
-        per_rank = (len(grid) + par.world_size - 1) // par.world_size
+        per_rank = max(len(o) for o in owners)
+        where = {idx: (src, slot) for src, o in enumerate(owners) for slot, idx in enumerate(o)}
         buf = torch.zeros(per_rank, self.config.out_channels, T_out, th, tw, dtype=torch.bfloat16, device=self.device)
         for slot, idx in enumerate(sorted(tiles)):
             t = tiles[idx]
@@ -387,7 +389,7 @@ class AutoencoderKLHunyuanVideo15:
         allbuf = par.allgather_frames(buf)
         out = {}
         for idx, (i, j) in enumerate(grid):
-            src, slot = idx % par.world_size, idx // par.world_size
+            src, slot = where[idx]
             hh, ww = min(tl, H - i) * r, min(tl, W - j) * r
             out[idx] = allbuf[src, slot, :, :, :hh, :ww].contiguous()
         return out

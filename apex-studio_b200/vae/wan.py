@@ -15,7 +15,8 @@ Design (DESIGN.md section "VAE"):
   ~60 launches per tile instead of ~35 convs x 21 frames;
 * the 32x32-latent / stride-24 tiling, the in-place blend order and the crop are reproduced exactly (tiles see zero
   padding at their borders in the reference, so decoding untiled would NOT give the same pixels);
-* tiles are independent until the blend: with N GPUs they are dealt round-robin and reassembled by ONE all-gather.
+* tiles are independent until the blend: with N GPUs they are dealt by cost (longest-processing-time first: the edge tiles are
+  smaller) and reassembled by ONE all-gather.
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .. import _lib, ops
-from ..parallel import ParallelContext, deal_round_robin
+from ..parallel import ParallelContext, deal_lpt
 
 
 @dataclass
@@ -403,14 +404,16 @@ class AutoencoderKLWan:
         ncols = len(range(0, W, sw // r))
         world = par.world_size if par is not None else 1
         rank = par.rank if par is not None else 0
-        mine = deal_round_robin(len(grid), world, rank)
+        # tiles are dealt by cost (latent pixels; the edge tiles of a 90 x 160 latent are up to 3.5 x smaller than a full one)
+        owners = deal_lpt([min(tmin_h, H - i) * min(tmin_w, W - j) for i, j in grid], world)
+        mine = owners[rank]
         T_out = 1 + self.config.scale_factor_temporal * (T - 1)
         tiles: Dict[int, torch.Tensor] = {}
         for idx in mine:
             i, j = grid[idx]
             tiles[idx] = self.decode_tile(z[:, :, i:i + tmin_h, j:j + tmin_w].contiguous())
         if world > 1:
-            tiles = self._allgather_tiles(tiles, grid, H, W, T_out, par)
+            tiles = self._allgather_tiles(tiles, grid, H, W, T_out, par, owners)
         frame = torch.empty(self.config.out_channels, T_out, H * r, W * r, dtype=torch.bfloat16, device=z.device)
         for idx, (i, j) in enumerate(grid):
             ri, cj = idx // ncols, idx % ncols
@@ -419,11 +422,12 @@ class AutoencoderKLWan:
             blend_tile(tiles[idx], up, left, frame, blend_h, sh, ri * sh, cj * sw)
         return frame
 
-    def _allgather_tiles(self, tiles, grid, H, W, T_out, par: ParallelContext):
+    def _allgather_tiles(self, tiles, grid, H, W, T_out, par: ParallelContext, owners):
         """Pad every rank's tiles to the full tile size, ONE all-gather, slice back to the true tile shapes."""
         r = self.spatial_compression_ratio
         th, tw = self.tile_sample_min_height, self.tile_sample_min_width
-        per_rank = (len(grid) + par.world_size - 1) // par.world_size
+        per_rank = max(len(o) for o in owners)
+        where = {idx: (src, slot) for src, o in enumerate(owners) for slot, idx in enumerate(o)}
         buf = torch.zeros(per_rank, self.config.out_channels, T_out, th, tw, dtype=torch.bfloat16, device=self.device)
         for slot, idx in enumerate(sorted(tiles)):
             t = tiles[idx]
@@ -431,7 +435,7 @@ class AutoencoderKLWan:
         allbuf = par.allgather_frames(buf)                                   # [world, per_rank, 3, T, th, tw]
         out = {}
         for idx, (i, j) in enumerate(grid):
-            src, slot = idx % par.world_size, idx // par.world_size
+            src, slot = where[idx]
             hh = min(th, (H - i) * r)
             ww = min(tw, (W - j) * r)
             out[idx] = allbuf[src, slot, :, :, :hh, :ww].contiguous()
