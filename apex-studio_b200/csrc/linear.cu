@@ -36,6 +36,10 @@ constexpr int BK = 64;
 constexpr int GROUP_M = 16;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
+// epilogue staging for the TMA-store path: per epilogue warp two [32 rows x 64 columns] bf16 boxes (128-byte rows, 128B swizzle)
+constexpr int EPI_BOX_BYTES = 32 * 128;
+constexpr int EPI_STAGING_BYTES = 4 * 2 * EPI_BOX_BYTES;
+constexpr bool TALL_BY_DEFAULT = false;   // set once measured on the B200 (profiles/r02_gemm_tall_ab.log)
 constexpr bool PAIR_BY_DEFAULT = true;    // validated on the B200: +10 % over the 1-CTA kernel (profiles/r01_gpu_session26_linear_pair.log)
 
 // NCTA = 1: one CTA per 128 x 256 output tile.  NCTA = 2 (cta_group::2): a CTA PAIR (cluster of 2 on one TPC) owns a
@@ -45,13 +49,20 @@ constexpr bool PAIR_BY_DEFAULT = true;    // validated on the B200: +10 % over t
 // BN_T: N extent of the output tile.  256 everywhere except the SMALL-M form <1, 64>: the 512-row text streams of the
 // dual-stream image models give only 24-96 tiles of 256 columns on 148 SMs; 64-column tiles quadruple the tile count
 // (profiles/r01_gemm_shapes_vs_cublas_pair.txt: 236-755 TFLOP/s on those shapes with 256-column tiles).
-template <int NCTA, int BN_T = BN>
+// TALL (NCTA = 2 only): every CTA owns 256 rows (two M = 128 halves, i.e. two M = 256 pair-MMAs per k-step into the two
+// halves of TMEM), so a CTA pair owns a 512 x 256 tile and each W byte is fetched once per 512 output rows: 96 KB from L2
+// per 512 x 256 x 64 block instead of 128 KB -- the traffic of the QUAD form, but on all 148 SMs.  Both 256-column
+// accumulators belong to ONE tile, so the epilogue (1.6k cycles) is no longer hidden behind the next tile's main loop
+// (82k cycles at K = 5120): a 2 % cost.  This is the tile shape cuBLAS picks for these GEMMs (nvjet 256x256_64x4 2cta,
+// profiles/r02_cublas_qkv_ncu.txt).
+template <int NCTA, int BN_T = BN, bool TALL = false>
 struct Cfg {
+  static constexpr int A_TILE_BYTES = A_BYTES * (TALL ? 2 : 1);
   static constexpr int B_ROWS = BN_T / NCTA;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = NCTA == 2 ? 6 : (BN_T == 64 ? 8 : 4);   // 64-column tiles: 128 MMA cycles per k-block, deeper ring
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+  static constexpr int STAGES = TALL ? 4 : (NCTA == 2 ? 6 : (BN_T == 64 ? 8 : 4));   // 64-column tiles: 128 MMA cycles per k-block, deeper ring
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 1024 /*barriers*/ + EPI_STAGING_BYTES;
 };
 
 struct Params {
@@ -63,6 +74,7 @@ struct Params {
   int epi;
   int bias_row;
   int tiles_m, tiles_n;
+  int tma_store; // 1: bf16 output written through shared memory + TMA (128-byte lines) instead of 16-byte stores per lane
   int group_m;   // row-tiles per rasterisation group (the A rows of a group stay in L2 while its n-tiles are swept)
   int panel_n;   // column-tiles per panel: the W panel (panel_n x BN x K) stays in L2 while ALL row groups sweep it
 };
@@ -100,13 +112,17 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 // shared memory (each CTA issues one 64-row box for itself and its counterpart in the other pair): L2 -> SM traffic per tile and
 // k-block drops from 64 KB to 48 KB.  A slot may only be refilled when BOTH pairs have consumed it: their commits are multicast
 // to all four CTAs and the `empty` barriers count two arrivals.
-template <int NCTA, int BN_T, bool QUAD = false>
+template <int NCTA, int BN_T, bool QUAD = false, bool TALL = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
+linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmC, Params p) {
   static_assert(!QUAD || NCTA == 2, "QUAD is a form of the CTA-pair kernel");
-  constexpr int STAGES = Cfg<NCTA, BN_T>::STAGES;
-  constexpr int STAGE_BYTES = Cfg<NCTA, BN_T>::STAGE_BYTES;
-  constexpr int B_ROWS = Cfg<NCTA, BN_T>::B_ROWS;
+  static_assert(!TALL || (NCTA == 2 && !QUAD && BN_T == BN), "TALL is a form of the plain CTA-pair kernel");
+  constexpr int STAGES = Cfg<NCTA, BN_T, TALL>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<NCTA, BN_T, TALL>::STAGE_BYTES;
+  constexpr int A_TILE_BYTES = Cfg<NCTA, BN_T, TALL>::A_TILE_BYTES;
+  constexpr int B_ROWS = Cfg<NCTA, BN_T, TALL>::B_ROWS;
+  constexpr int ROWS_PER_CTA = TALL ? 2 * BM : BM;
   constexpr int CLUSTER = QUAD ? 4 : NCTA;
   const uint32_t cl_rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank inside the cluster
   const uint32_t cta_rank = cl_rank & 1u;                         // rank inside the CTA pair
@@ -120,6 +136,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* acc_full = bars + 2 * STAGES;   // [2]
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES + 1024;   // 1024-aligned: a swizzle atom is 8 rows x 128 B
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,7 +186,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int kb = 0; kb < num_kb; ++kb) {
           lin_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
           if constexpr (NCTA == 2) {
             // both CTAs fill their own shared memory; the bytes of both complete on the LEADER's barrier.  The peer never
             // arrives: it may only refill a slot after the leader's MMAs of the previous round were committed (its own
@@ -184,7 +201,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                  (tm * 2 + static_cast<int>(cta_rank)) * BM + static_cast<int>(pair_id) * (BM / 2), mc);
               tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, (tn * 2 + static_cast<int>(pair_id)) * BN_T + static_cast<int>(cta_rank) * B_ROWS);
             } else {
-              tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * BM);
+              // TALL: one box of 256 rows (the tensor map's box is ROWS_PER_CTA tall)
+              tma_load_2d_2sm(sa, &tmA, lbar, kb * BK, (tm * 2 + static_cast<int>(cta_rank)) * ROWS_PER_CTA);
               tma_load_2d_2sm(sb, &tmB, lbar, kb * BK, tn * BN_T + static_cast<int>(cta_rank) * B_ROWS);
             }
           } else {
@@ -207,8 +225,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t phase = 0;
       int it = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        // TALL: ONE accumulator set (both 256-column halves belong to this tile), phase = tile parity
+        const int acc = TALL ? 0 : (it & 1);
+        const uint32_t acc_phase = TALL ? (it & 1) : ((it >> 1) & 1);
         lin_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -216,13 +235,17 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           lin_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TALL) {   // rows 128..255 of both CTAs -> TMEM columns 256..511
+              const uint64_t da2 = make_smem_desc_sw128(a_addr + A_BYTES + k * 32, 16, 1024);
+              umma_ss_2sm(d_tmem + BN, da2, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (QUAD) umma_commit_2sm_mask(&empty[stage], 0xF);       // all four CTAs: a slot is shared by both pairs
           else if constexpr (NCTA == 2) umma_commit_2sm(&empty[stage]);
@@ -242,13 +265,88 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, p.panel_n, tm, tn);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = TALL ? 0 : (it & 1);
+      const uint32_t acc_phase = TALL ? (it & 1) : ((it >> 1) & 1);
       lin_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int row = (tm * NCTA + static_cast<int>(cta_rank)) * BM + quad * 32 + lane;
+#pragma unroll 1
+      for (int half = 0; half < (TALL ? 2 : 1); ++half) {
+      const int row = (tm * NCTA + static_cast<int>(cta_rank)) * ROWS_PER_CTA + half * BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc + half) * BN;
+      if (p.tma_store) {
+        // Output through shared memory + TMA: every lane owns ONE row of the accumulator, so direct stores are 32 scattered
+        // 16-byte pieces per instruction (262,144 L2 write transactions per 256 x 256 tile -- more than the whole operand
+        // stream); here a warp stages [32 rows x 64 columns] (128-byte rows, 128B swizzle = conflict-free 16-byte chunks)
+        // and one elected lane issues a bulk tensor store of full 128-byte lines; the M / N tails are clipped by the TMA unit.
+        uint8_t* my_stage = epi_stage + (warp - 2) * 2 * EPI_BOX_BYTES;
+        const int row_base = row - lane;
+#pragma unroll 1
+        for (int c = 0; c < BN_T / 64; ++c) {
+          const int col0 = (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn) * BN_T + c * 64;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r0[32], r1[32];
+          tmem_ld_x32(t_addr + c * 64, r0);
+          tmem_ld_x32(t_addr + c * 64 + 32, r1);
+          tmem_ld_wait();
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+          if (p.bias != nullptr && p.bias_row) {
+            const float br = row_ok ? __bfloat162float(p.bias[row]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] += br;
+          } else if (p.bias != nullptr) {
+            if (col0 + 64 <= p.N) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const uint4 b = __ldg(bp + q4);
+                v[q4 * 8 + 0] += bf16_lo(b.x); v[q4 * 8 + 1] += bf16_hi(b.x);
+                v[q4 * 8 + 2] += bf16_lo(b.y); v[q4 * 8 + 3] += bf16_hi(b.y);
+                v[q4 * 8 + 4] += bf16_lo(b.z); v[q4 * 8 + 5] += bf16_hi(b.z);
+                v[q4 * 8 + 6] += bf16_lo(b.w); v[q4 * 8 + 7] += bf16_hi(b.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j)
+                if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+            }
+          }
+          if (p.epi == B200_EPI_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
+          } else if (p.epi == B200_EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+          } else if (p.epi == B200_EPI_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+          }
+          uint8_t* box = my_stage + (c & 1) * EPI_BOX_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();     // the store that last read this box (two chunks ago) has drained it
+          __syncwarp();
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            uint4 o;
+            o.x = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]);
+            o.y = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
+            o.z = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]);
+            o.w = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
+            *reinterpret_cast<uint4*>(box + lane * 128 + ((q4 ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, box, col0, row_base);
+            tma_store_commit();
+          }
+        }
+        continue;   // next half / tile
+      }
 #pragma unroll 1
       for (int c = 0; c < BN_T / 32; ++c) {
         const int col0 = (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn) * BN_T + c * 32;
@@ -359,6 +457,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       }
+      }   // half
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -366,6 +465,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         else mbar_arrive(&acc_empty[acc]);
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait<0>();   // bulk stores read shared memory: drain before the CTA exits
   }
 
   tc_fence_before();
@@ -425,13 +525,22 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     quad_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
   }
   const int64_t pair_tiles = static_cast<int64_t>((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
-  const bool use_quad = use_pair && ((N + BN - 1) / BN) >= 2 && (quad_mode == 1 || (quad_mode == -1 && pair_tiles >= 1000));
+  // TALL (512 x 256 tile per CTA pair, see Cfg): B200_LINEAR_TALL=1 / 0 forces / disables it
+  static int tall_mode = -2;
+  if (tall_mode == -2) {
+    const char* ev = getenv("B200_LINEAR_TALL");
+    tall_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+  }
+  const bool use_tall = use_pair && (tall_mode == 1 || (tall_mode == -1 && TALL_BY_DEFAULT && pair_tiles >= 1000));
+  const bool use_quad = !use_tall && use_pair && ((N + BN - 1) / BN) >= 2 &&
+                        (quad_mode == 1 || (quad_mode == -1 && pair_tiles >= 1000));
+  const int rows_per_cta = use_tall ? 2 * BM : BM;
 
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t str[2] = {1, (uint64_t)lda};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(use_quad ? BM / 2 : BM)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(use_quad ? BM / 2 : rows_per_cta)};
     int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -442,7 +551,24 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box);
     if (rc) return rc;
   }
+  // TMA-store epilogue for the bf16, non-residual epilogues (B200_LINEAR_TMA_STORE=0 disables)
+  static int tma_store_mode = -2;
+  if (tma_store_mode == -2) {
+    const char* ev = getenv("B200_LINEAR_TMA_STORE");
+    tma_store_mode = ev ? (ev[0] == '1' ? 1 : 0) : 1;
+  }
+  const bool use_tma_store = tma_store_mode == 1 && epilogue != B200_EPI_GATE_RES && epilogue != B200_EPI_BIAS_F32 && N >= 64;
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  if (use_tma_store) {
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t str[2] = {1, (uint64_t)ldc};
+    uint32_t box[2] = {64, 32};
+    int rc = make_tmap_bf16(&tmC, C, 2, dims, str, box);
+    if (rc) return rc;
+  }
   Params p;
+  p.tma_store = use_tma_store ? 1 : 0;
   p.M = M; p.N = N; p.K = K;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
@@ -450,7 +576,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.ldc = ldc;
   p.epi = epilogue;
   p.bias_row = bias_row;
-  p.tiles_m = (M + BM * ncta - 1) / (BM * ncta);
+  p.tiles_m = (M + rows_per_cta * ncta - 1) / (rows_per_cta * ncta);
   p.tiles_n = (N + bn - 1) / bn;
   if (use_quad) p.tiles_n = (p.tiles_n + 1) / 2;      // column tile PAIRS
   {
@@ -458,7 +584,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     // of equal width (see tile_coords).
     // Measured effect under the power cap: within +-3 % of the round-1 order on every Wan shape (profiles/r02_gemm_raster_sweep.log)
     // -- HBM traffic drops 3x but the kernel is bound by energy per FLOP elsewhere.
-    const double row_tile_bytes = 2.0 * BM * ncta * K, col_tile_bytes = 2.0 * bn * (use_quad ? 2 : 1) * K;
+    const double row_tile_bytes = 2.0 * rows_per_cta * ncta * K, col_tile_bytes = 2.0 * bn * (use_quad ? 2 : 1) * K;
     int gm = static_cast<int>(24.0e6 / row_tile_bytes);
     int pn = static_cast<int>(64.0e6 / col_tile_bytes);
     p.group_m = gm < 4 ? 4 : (gm > GROUP_M ? GROUP_M : gm);
@@ -478,7 +604,8 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
         return cudaFuncSetAttribute(linear_kernel<1, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess &&
                cudaFuncSetAttribute(linear_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1, 64>::SMEM_BYTES) == cudaSuccess &&
                cudaFuncSetAttribute(linear_kernel<2, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess &&
-               cudaFuncSetAttribute(linear_kernel<2, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+               cudaFuncSetAttribute(linear_kernel<2, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess &&
+               cudaFuncSetAttribute(linear_kernel<2, BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2, BN, true>::SMEM_BYTES) == cudaSuccess;
       }))
     return B200_ERR_LAUNCH;
   if (use_quad) {
@@ -506,7 +633,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     }
     const int quads = total < fit ? total : fit;
     cfg.gridDim = dim3(4 * quads, 1, 1);
-    if (cudaLaunchKernelEx(&cfg, linear_kernel<2, BN, true>, tmA, tmB, p) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, linear_kernel<2, BN, true>, tmA, tmB, tmC, p) != cudaSuccess) {
       cudaGetLastError();
       return B200_ERR_LAUNCH;
     }
@@ -517,7 +644,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = use_tall ? Cfg<2, BN, true>::SMEM_BYTES : Cfg<2>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -533,14 +660,16 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
       fprintf(stderr, "[apex_b200] linear pair kernel: max active clusters %d (err %d), launching %d pairs\n", ncl, (int)e, pairs);
       dbg_done = true;
     }
-    if (cudaLaunchKernelEx(&cfg, linear_kernel<2, BN>, tmA, tmB, p) != cudaSuccess) {
+    const cudaError_t le = use_tall ? cudaLaunchKernelEx(&cfg, linear_kernel<2, BN, false, true>, tmA, tmB, tmC, p)
+                                    : cudaLaunchKernelEx(&cfg, linear_kernel<2, BN>, tmA, tmB, tmC, p);
+    if (le != cudaSuccess) {
       cudaGetLastError();
       return B200_ERR_LAUNCH;
     }
   } else {
     const int grid = total < num_sms() ? total : num_sms();
-    if (small_m) linear_kernel<1, 64><<<grid, NUM_THREADS, Cfg<1, 64>::SMEM_BYTES, st>>>(tmA, tmB, p);
-    else linear_kernel<1, BN><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB, p);
+    if (small_m) linear_kernel<1, 64><<<grid, NUM_THREADS, Cfg<1, 64>::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
+    else linear_kernel<1, BN><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
   }
   B200_CHECK_LAUNCH();
   return B200_OK;

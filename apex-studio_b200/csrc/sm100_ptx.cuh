@@ -136,6 +136,11 @@ B200_DEVICE void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, in
       "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+B200_DEVICE void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
 B200_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 B200_DEVICE void tma_store_wait_read() {
