@@ -15,6 +15,26 @@ LIB_PATH = os.environ.get("APEX_B200_LIB") or os.path.join(_HERE, "libapex_b200.
 
 _i, _i64, _f, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
+class WanResBlock(ctypes.Structure):
+    _fields_ = [(n, _p) for n in ("norm1_gamma", "conv1_w", "conv1_b", "norm2_gamma", "conv2_w", "conv2_b", "shortcut_w", "shortcut_b")] + \
+               [("cin", _i), ("cout", _i)]
+
+
+class WanAttn(ctypes.Structure):
+    _fields_ = [(n, _p) for n in ("norm_gamma", "to_qkv_w", "to_qkv_b", "proj_w", "proj_b")] + [("channels", _i)]
+
+
+class WanUpsample(ctypes.Structure):
+    _fields_ = [(n, _p) for n in ("resample_w", "resample_b", "time_conv_w", "time_conv_b")] + [("channels", _i), ("temporal", _i)]
+
+
+class WanVaeWeights(ctypes.Structure):
+    """B200WanVaeWeights of include/apex_b200.h"""
+    _fields_ = [("post_quant_w", _p), ("post_quant_b", _p), ("conv_in_w", _p), ("conv_in_b", _p), ("mid_res", WanResBlock * 2),
+                ("mid_attn", WanAttn), ("up_res", (WanResBlock * 3) * 4), ("up_samp", WanUpsample * 3), ("norm_out_gamma", _p),
+                ("conv_out_w", _p), ("conv_out_b", _p), ("dims", _i * 5), ("z_pad", _i)]
+
+
 # name -> (restype, argtypes); must list every symbol include/apex_b200.h declares.
 SIGNATURES = {
     "b200_version": (_i, []),
@@ -44,6 +64,8 @@ SIGNATURES = {
     "b200_dcae_upsample_cl": (_i, [_p, _p, _p] + [_i] * 6 + [_p]),
     "b200_softmax_rows_block_causal": (_i, [_p, _p, _i, _i, _i64, _i64, _f, _i, _p]),
     "b200_blend_tile_noclamp": (_i, [_p, _p, _p, _p] + [_i] * 14 + [_p]),
+    "b200_wan_vae_decode_workspace": (_i64, [ctypes.POINTER(WanVaeWeights), _i, _i, _i]),
+    "b200_wan_vae_decode": (_i, [_p, ctypes.POINTER(WanVaeWeights), _p, _p, _i64, _i, _i, _i, _p]),
     "b200_ln_modulate": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
     "b200_qkv_rmsnorm_rope": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i64, _f, _p]),
     "b200_mlp_gelu": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),

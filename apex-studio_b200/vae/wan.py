@@ -223,6 +223,7 @@ class AutoencoderKLWan:
             else:
                 w[k] = v.to(bf).contiguous()
         self.w = w
+        self._cw = None
         return [], []
 
     def init_random_weights(self, device="cuda", seed: int = 7):
@@ -344,8 +345,84 @@ class AutoencoderKLWan:
         u = upsample2x_cl(x)
         return conv3d_cl(u, w[p + ".resample.1.weight"], w[p + ".resample.1.bias"], (1, 3, 3), C // 2)
 
+    # -------------------------------------------------------------------------------- one C call per tile
+    def _c_weights(self) -> "_lib.WanVaeWeights":
+        """The B200WanVaeWeights table (include/apex_b200.h) over the resident weights; built once per load."""
+        if getattr(self, "_cw", None) is not None:
+            return self._cw
+        w, c = self.w, self.config
+        if len(c.dim_mult) != 4 or c.num_res_blocks != 2:
+            raise ValueError("b200_wan_vae_decode covers the 4-stage / 3-residual-block decoder of the Wan 2.1 / 2.2 VAE")
+        ptr = lambda k: w[k].data_ptr() if k in w else None
+        cw = _lib.WanVaeWeights()
+        cw.post_quant_w, cw.post_quant_b = ptr("post_quant_conv.weight"), ptr("post_quant_conv.bias")
+        cw.conv_in_w, cw.conv_in_b = ptr("decoder.conv_in.weight"), ptr("decoder.conv_in.bias")
+
+        def res(dst, p):
+            dst.norm1_gamma, dst.norm2_gamma = ptr(p + ".norm1.gamma"), ptr(p + ".norm2.gamma")
+            dst.conv1_w, dst.conv1_b = ptr(p + ".conv1.weight"), ptr(p + ".conv1.bias")
+            dst.conv2_w, dst.conv2_b = ptr(p + ".conv2.weight"), ptr(p + ".conv2.bias")
+            dst.shortcut_w, dst.shortcut_b = ptr(p + ".conv_shortcut.weight"), ptr(p + ".conv_shortcut.bias")
+            dst.cin, dst.cout = w[p + ".norm1.gamma"].numel(), w[p + ".conv1.bias"].numel()
+
+        res(cw.mid_res[0], "decoder.mid_block.resnets.0")
+        res(cw.mid_res[1], "decoder.mid_block.resnets.1")
+        a = "decoder.mid_block.attentions.0"
+        cw.mid_attn.norm_gamma, cw.mid_attn.to_qkv_w, cw.mid_attn.to_qkv_b = ptr(a + ".norm.gamma"), ptr(a + ".to_qkv.weight"), ptr(a + ".to_qkv.bias")
+        cw.mid_attn.proj_w, cw.mid_attn.proj_b, cw.mid_attn.channels = ptr(a + ".proj.weight"), ptr(a + ".proj.bias"), self.dims[0]
+        for i in range(4):
+            for j in range(3):
+                res(cw.up_res[i][j], f"decoder.up_blocks.{i}.resnets.{j}")
+            if i != 3:
+                u = f"decoder.up_blocks.{i}.upsamplers.0"
+                cw.up_samp[i].resample_w, cw.up_samp[i].resample_b = ptr(u + ".resample.1.weight"), ptr(u + ".resample.1.bias")
+                cw.up_samp[i].time_conv_w, cw.up_samp[i].time_conv_b = ptr(u + ".time_conv.weight"), ptr(u + ".time_conv.bias")
+                cw.up_samp[i].channels = w[u + ".resample.1.bias"].numel() * 2
+                cw.up_samp[i].temporal = int(bool(self.temporal_upsample[i]))
+        cw.norm_out_gamma = ptr("decoder.norm_out.gamma")
+        cw.conv_out_w, cw.conv_out_b = ptr("decoder.conv_out.weight"), ptr("decoder.conv_out.bias")
+        for i, d in enumerate(self.dims):
+            cw.dims[i] = d
+        cw.z_pad = self.z_pad
+        self._cw = cw
+        return cw
+
     def decode_tile(self, z: torch.Tensor) -> torch.Tensor:
-        """z [zc, T, h, w] (one latent tile, all frames) -> planar bf16 [3, 1+4(T-1), 8h, 8w] (pre-clamp)."""
+        """z [zc, T, h, w] (one latent tile, all frames) -> planar bf16 [3, 1+4(T-1), 8h, 8w] (pre-clamp) through ONE C call,
+        ``b200_wan_vae_decode`` (the whole launch sequence of the decoder is issued from C into a reusable workspace);
+        bit-identical to ``decode_tile_py``, which issues the same kernels one by one."""
+        import ctypes
+
+        zc, T, h, wd = z.shape
+        x = torch.zeros(T, h, wd, 64, dtype=torch.bfloat16, device=z.device)               # K padded to one tile
+        x[..., :zc] = z.permute(1, 2, 3, 0)
+        cw = self._c_weights()
+        lib = _lib.load()
+        need = lib.b200_wan_vae_decode_workspace(ctypes.byref(cw), T, h, wd)
+        if need < 0:
+            _lib.check(int(need), "b200_wan_vae_decode_workspace")
+        ws = getattr(self, "_tile_ws", None)
+        if ws is None or ws.numel() < need or ws.device != z.device:
+            self._tile_ws = ws = torch.empty(int(need), dtype=torch.uint8, device=z.device)
+        T_out = 1 + self.config.scale_factor_temporal * (T - 1) if T > 1 else 1
+        r = self.spatial_compression_ratio
+        out = torch.empty(self.config.out_channels, T_out, h * r, wd * r, dtype=torch.bfloat16, device=z.device)
+        rc = lib.b200_wan_vae_decode(x.data_ptr(), ctypes.byref(cw), out.data_ptr(), ws.data_ptr(), ws.numel(), T, h, wd, _stream())
+        _lib.check(rc, "b200_wan_vae_decode")
+        ops._count(self._tile_launches(T))
+        return out
+
+    def _tile_launches(self, T: int) -> int:
+        """kernels b200_wan_vae_decode enqueues for a T-frame tile: post_quant + conv_in + conv_out + norm_out (4), 14 residual
+        blocks x 4 (+1 per shortcut), the mid attention (1 + 6 per frame), 3 upsamplers x 2 (+1 time_conv each when T > 1)"""
+        w = self.w
+        n = 4 + 14 * 4 + sum(1 for k in w if k.endswith("conv_shortcut.weight")) + 1 + 6 * T + 3 * 2
+        if T > 1:
+            n += sum(1 for t in self.temporal_upsample if t)
+        return n
+
+    def decode_tile_py(self, z: torch.Tensor) -> torch.Tensor:
+        """The same decode issued kernel by kernel from Python (round-1 path; kept as the differential partner of the C entry)."""
         w = self.w
         zc, T, h, wd = z.shape
         x = torch.zeros(T, h, wd, 64, dtype=torch.bfloat16, device=z.device)               # K padded to one tile

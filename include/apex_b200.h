@@ -271,6 +271,48 @@ int b200_blend_tile_noclamp(void* tile, const void* up, const void* left, void* 
                             int up_h, int up_w, int left_h, int left_w, int blend, int crop_h, int crop_w, int y0, int x0,
                             int OH, int OW, void* stream);
 
+/*
+ * The whole Wan 3D-VAE decoder of ONE latent tile in one call (SURVEY.md section 8b minimum set: b200_wan_vae_decode <-
+ * AutoencoderKLWan.decode, vae/wan/model.py:1378 -> _decode :1333-1375 -> post_quant_conv + WanDecoder3d.forward :972-1021
+ * over all latent frames; the reference streams frame by frame through feat_cache, which equals one causal pass over the
+ * whole time axis -- tests/test_oracle_vae.py).  Non-residual decoder (Wan 2.1 / 2.2-A14B): conv_in, mid block (res, single-head
+ * attention, res), four up blocks of three residual blocks, three upsamplers, norm_out + conv_out.  All pointers are bf16 device
+ * memory in the layouts AutoencoderKLWan.load_state_dict of this package produces: conv weights tap-major [taps * Cout, Cin],
+ * 1x1 convs as [Cout, Cin], gammas [C].
+ *   z_cl       [T, h, w, 64]   the latent tile channels-last, z_dim real channels + zero padding to 64
+ *   out        [3, 1 + 4 (T - 1), 8 h, 8 w]   planar bf16, BEFORE the clamp (the blend kernel clamps)
+ *   workspace  >= b200_wan_vae_decode_workspace(...) bytes, 256-byte aligned; nothing is allocated inside
+ * ~197 launches for a 32 x 32 x 21 tile, all on `stream`.
+ */
+typedef struct {
+  const void *norm1_gamma, *conv1_w, *conv1_b, *norm2_gamma, *conv2_w, *conv2_b;
+  const void *shortcut_w, *shortcut_b; /* 1x1 conv [cout, cin] when cin != cout, else NULL */
+  int cin, cout;
+} B200WanResBlock;
+typedef struct {
+  const void *norm_gamma, *to_qkv_w, *to_qkv_b, *proj_w, *proj_b; /* to_qkv [3C, C], proj [C, C] */
+  int channels;
+} B200WanAttn;
+typedef struct {
+  const void *resample_w, *resample_b;   /* (1,3,3) conv C -> C/2, tap-major */
+  const void *time_conv_w, *time_conv_b; /* (3,1,1) conv C -> 2C (temporal upsample) or NULL */
+  int channels, temporal;
+} B200WanUpsample;
+typedef struct {
+  const void *post_quant_w, *post_quant_b; /* [z_pad, 64], [z_pad] */
+  const void *conv_in_w, *conv_in_b;       /* [27 * dims[0], z_pad] */
+  B200WanResBlock mid_res[2];
+  B200WanAttn mid_attn;
+  B200WanResBlock up_res[4][3];
+  B200WanUpsample up_samp[3];
+  const void *norm_out_gamma, *conv_out_w, *conv_out_b; /* conv_out padded to 16 output channels */
+  int dims[5];                             /* decoder widths, e.g. 384 384 384 192 96 */
+  int z_pad;                               /* channels conv_in consumes (32) */
+} B200WanVaeWeights;
+int64_t b200_wan_vae_decode_workspace(const B200WanVaeWeights* w, int T, int h, int wd);
+int b200_wan_vae_decode(const void* z_cl, const B200WanVaeWeights* w, void* out, void* workspace, int64_t workspace_bytes,
+                        int T, int h, int wd, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Composite entry points at the granularity of the reference's call sites.  Each enqueues the
  * kernels above back to back on `stream`; tensors are contiguous ([rows, dim] unless a stride is given).

@@ -4,5 +4,5 @@ set -e
 cd "$(dirname "$0")/../apex-studio_b200/csrc"
 tag=$1; shift
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -c attention.cu -o /tmp/attention_$tag.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libapex_b200_$tag.so abi.o elementwise.o linear.o /tmp/attention_$tag.o conv.o vae_ops.o mmdit_ops.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libapex_b200_$tag.so abi.o elementwise.o linear.o /tmp/attention_$tag.o conv.o vae_ops.o mmdit_ops.o wan_vae.o -lcudart
 echo built libapex_b200_$tag.so

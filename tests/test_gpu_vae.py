@@ -153,6 +153,21 @@ def test_blend_tile_matches_reference_order():
     assert torch.equal(frame.cpu(), expect)
 
 
+@pytest.mark.parametrize("base_dim,shape", [(32, (16, 3, 12, 20)), (32, (16, 1, 8, 8)), (96, (16, 2, 18, 16)), (32, (16, 5, 32, 32))])
+def test_c_entry_tile_decode_is_bit_identical_to_the_per_kernel_path(base_dim, shape):
+    """b200_wan_vae_decode (ONE C call: the whole decoder launch sequence into a ping-pong workspace) vs the same kernels
+    issued one by one from Python: identical bits, for ragged tiles, a single frame (no temporal upsampling) and width 96."""
+    from apex_studio_b200.vae import AutoencoderKLWan, WanVAEConfig
+
+    vae = AutoencoderKLWan(WanVAEConfig(base_dim=base_dim))
+    vae.load_state_dict(wan_vae.make_weights(base_dim=base_dim, seed=3), device=DEV)
+    z = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).to(DEV, torch.bfloat16)
+    a = vae.decode_tile(z)
+    b = vae.decode_tile_py(z)
+    assert a.shape == b.shape and torch.equal(a, b)
+    assert torch.equal(vae.decode_tile(z), a)              # workspace reuse
+
+
 @pytest.mark.parametrize("name,tiling,sub", [("untiled", False, 2), ("tiled", True, 3)])
 def test_vae_decode_vs_reference_golden(name, tiling, sub):
     from apex_studio_b200.vae import AutoencoderKLWan, WanVAEConfig
