@@ -129,16 +129,16 @@ def cpu_reference_sample(n_tok: int = 256, repeats: int = 1):
     v = torch.randn(1, HEADS, S_TOKENS, 128, generator=g).to(bf)
     with torch.inference_mode():
         wan_dit.block_forward(h[:, :16], ctx, temb6, freqs[:16], w, "blocks.0", HEADS)  # warm-up
-        ta = tb = 0.0
+        tas, tbs = [], []
         for _ in range(repeats):
             t0 = time.perf_counter()
             wan_dit.block_forward(h, ctx, temb6, freqs, w, "blocks.0", HEADS)
             t1 = time.perf_counter()
             wan_dit.sdpa(q, k, v)
             t2 = time.perf_counter()
-            ta += t1 - t0
-            tb += t2 - t1
-    ta, tb = ta / repeats, tb / repeats
+            tas.append(t1 - t0)
+            tbs.append(t2 - t1)
+    ta, tb = statistics.median(tas), statistics.median(tbs)     # median of the repeats: the host cores are shared
     scale = S_TOKENS / n_tok
     step_s = (ta + tb) * scale * LAYERS * 2
     sample = (f"1 WanTransformerBlock (d=5120, ffn=13824, 40 heads, bf16, torch CPU) on {n_tok} query tokens: token-wise ops "
@@ -157,7 +157,7 @@ def run_reference_arm(args):
     for _ in range(max(1, args.warmup // 3)):
         cpu_reference_sample(n_tok=64)
     for _ in range(args.steps):
-        vals.append(cpu_reference_sample(n_tok=2048))
+        vals.append(cpu_reference_sample(n_tok=4096, repeats=3))   # ~5-8 s of host work per step, median of 3
     v = statistics.mean(x["value"] for x in vals)
     base = dict(vals[-1], value=v)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -422,7 +422,7 @@ def run_b200_arm(args):
             line["reference_gpu"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_reference_sample(n_tok=2048, repeats=2)
+            line["cpu_baseline"] = cpu_reference_sample(n_tok=4096, repeats=3)
         except Exception as e:  # keep the GPU line even if the host is too small for the sample
             line["cpu_baseline"] = {"error": repr(e)}
     emit(line)
