@@ -68,26 +68,41 @@ constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 // (216/80 = 512 deadlocked every CTA in bring-up).
 constexpr int REGS_SOFTMAX = 208;
 constexpr int REGS_OTHER = 88;
+constexpr int STAGE_MAX_KV_TILES = 8;     // staged epilogue + 3-slot ring up to this many key tiles (Wan cross-attention: 4)
+constexpr int MULTI_MAX_KV_TILES = 128;    // persistent launch up to this many key tiles per work item
 constexpr bool PAIR_BY_DEFAULT = false;   // CTA pairs: set once measured faster than single CTAs on the B200
 static_assert(2 * REGS_SOFTMAX + REGS_OTHER <= 504, "setmaxnreg.inc would wait forever");
 
-template <int NCTA>
+// STAGE (1-CTA, decoupled pipeline): the epilogue stages O in shared memory and writes it with TMA bulk stores instead of
+// 16-byte stores per lane.  One thread owns one output ROW (= TMEM lane), so a warp-wide 16-byte store touches 32 different
+// 128-byte lines: 512 line accesses per warp and tile, ~6,000 cycles of LSU time per work item (measured with the in-kernel
+// timeline: profiles/r02_attn_cross_timeline.log) -- irrelevant next to 591 key tiles, but 1/3 of a 4-key-tile
+// cross-attention item.  The staging area (8 warps x two [32 rows x 64 channels] boxes = 64 KB) takes the place of TWO K/V ring
+// slots (3 remain: K runs one tile ahead instead of two), so this form is used for short key sequences only -- their K/V
+// come from L2.
+template <int NCTA, bool STAGE = false>
 struct Cfg {
   static constexpr int KV_BYTES = TILE_BYTES / NCTA;   // bytes of one K (or V) tile staged by ONE CTA
   // ring depth: the decoupled pipeline issues S_t(j+2) while V_j is still in use, so K_{j+2} must land about one key tile
   // ahead -- 5 slots of 32 KB (4 stalled the MMA issuer ~800 cycles per key tile on the K wait: profiles/r02_attn_timeline_*.log)
-  static constexpr int KV_SLOTS = NCTA == 2 ? 8 : 5;
-  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * KV_BYTES + 1024 + 256;
+  static constexpr int KV_SLOTS = NCTA == 2 ? 8 : (STAGE ? 3 : 5);
+  static constexpr int STAGE_BYTES = STAGE ? 8 * 8192 : 0;
+  static constexpr int SMEM_BYTES = 2 * TILE_BYTES + KV_SLOTS * KV_BYTES + STAGE_BYTES + 1024 + 256;
 };
 
 struct Params {
   int B, H, Sq, Sk;
+  int n_kv;           // key tiles: ceil(Sk / 128)
+  int n_qt;           // query tile groups per (batch, head): ceil(Sq / (2 * BQ * NCTA))
+  int n_hb;           // H * B
+  int n_items;        // n_qt * H * B work items; a CTA (pair) walks items blockIdx.x / NCTA + i * gridDim.x / NCTA
   __nv_bfloat16* o;
   int64_t o_sb, o_sh, o_ss;
   float scale_log2;
   // Sequence-parallel "heads -> tokens" exchange fused into the epilogue: query row r belongs to the rank that owns
   // token r, so its output row is stored straight into that peer's [S/P, H_total*128] buffer over NVLink.
   void* o_peer[8];
+  int o_vec32;        // every output row is 32-byte aligned: the direct-store epilogue may use 32-byte stores
   int n_peers;        // 0 = plain store into `o`
   int rows_per_rank;  // S / P
   int head_off;       // first global head computed by this rank
@@ -150,22 +165,29 @@ B200_DEVICE float fmax3(float a, float b, float c) {
 #endif
 constexpr int POLY_PAIRS = ATTN_POLY_PAIRS;  // of every 16 column pairs (32 columns) -> 25 % of the exps leave the SFU
 
-#define ATTN_STAMP(step, k)                                                                     \
-  do {                                                                                         \
-    if (PROF && prof_cta && (step) < p.prof_steps) p.prof[(step) * 32 + (k)] = clock64();       \
+// row = key-tile step counted over all work items of CTA 0 (n_steps is the role's running step count)
+#define ATTN_STAMP(step, k)                                                                                       \
+  do {                                                                                                           \
+    if (PROF && prof_cta && (n_steps + (step)) < p.prof_steps) p.prof[(n_steps + (step)) * 32 + (k)] = clock64(); \
   } while (0)
 
-template <int NCTA, int PIPE, bool PROF = false>
+// MULTI: the CTA walks several work items (persistent launch).  Without it the item loops run exactly once and the
+// cross-item bookkeeping folds away at compile time: the long self-attention launches (591 key tiles per item, prologue
+// amortised) keep the leaner single-item issue loop.
+template <int NCTA, int PIPE, bool PROF = false, bool STAGE = false, bool MULTI = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, Params p) {
-  constexpr int KV_SLOTS = Cfg<NCTA>::KV_SLOTS;
-  constexpr int KV_BYTES = Cfg<NCTA>::KV_BYTES;
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, Params p) {
+  static_assert(!STAGE || (NCTA == 1 && PIPE == 1), "staged epilogue: 1-CTA decoupled pipeline only");
+  static_assert(!MULTI || (NCTA == 1 && PIPE == 1), "persistent launch: 1-CTA decoupled pipeline only");
+  constexpr int KV_SLOTS = Cfg<NCTA, STAGE>::KV_SLOTS;
+  constexpr int KV_BYTES = Cfg<NCTA, STAGE>::KV_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                      // 2 tiles
   uint8_t* kv_smem = smem + 2 * TILE_BYTES;    // KV_SLOTS slots
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + KV_SLOTS * KV_BYTES);
+  uint8_t* o_stage = kv_smem + KV_SLOTS * KV_BYTES;   // STAGE: two 4 KB boxes per softmax warp (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_stage + Cfg<NCTA, STAGE>::STAGE_BYTES);
   uint64_t* q_full = bars;                 // [1]          (pair: the leader's collects both CTAs' bytes)
   uint64_t* kv_full = bars + 1;            // [KV_SLOTS]   (pair: leader's)
   uint64_t* kv_empty = kv_full + KV_SLOTS; // [KV_SLOTS]   (pair: multicast commit -> both CTAs)
@@ -173,7 +195,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = s_full + 2;           // [2]          (pair: leader's, 4 local + 4 remote warps arrive)
   uint64_t* o_done = p_full + 2;           // [2]          (multicast)
   uint64_t* s_free = o_done + 2;           // [1]  PIPE 1: the shared S buffer has been pulled into registers (pair: leader's)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + 1);
+  uint64_t* q_empty = s_free + 1;          // [1]  persistent: the last S MMA of a work item has read the Q tiles
+  uint64_t* o_free = q_empty + 1;          // [2]  persistent: the epilogue of tile t has read O_t out of TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
   // TMEM columns
   constexpr uint32_t S_COL0 = 0, S_COL1 = PIPE ? 0 : 128;                  // PIPE 1: one S buffer for both tiles
   constexpr uint32_t P_COL0 = PIPE ? 128 : 0, P_COL1 = PIPE ? 192 : 128;   // PIPE 0: P_t aliases S_t
@@ -183,18 +207,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int n_kv = (p.Sk + BKV - 1) / BKV;
-  const bool prof_cta = PROF && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-  // first query row of tile t of this CTA: a pair owns 2 * 256 rows, MMA tile t = rows [t * 256, +256) of them
-  const int row_base = static_cast<int>(blockIdx.x / NCTA) * (2 * BQ * NCTA) + static_cast<int>(cta_rank) * BQ;
+  // (n_kv = p.n_kv, w_step and p.n_items are read from the constant bank where used: as locals computed up here they
+  // were spilled across the role split and re-loaded from local memory inside the MMA issuer's loop)
+#define n_kv (p.n_kv)
+#define w_step (static_cast<int>(gridDim.x / NCTA))
+  // Work items (query tile group, head, batch), query tiles fastest so that the CTAs resident at any moment share one
+  // head's K/V in L2.  A non-persistent launch has one item per CTA (pair); a persistent launch (1-CTA, PIPE 1) has one
+  // CTA per SM walking items w0, w0 + w_step, ...: barriers, TMEM and descriptors are set up once, and the Q / K loads
+  // and the first S MMAs of the next item run under the epilogue of the current one.
+  const int w0 = static_cast<int>(blockIdx.x / NCTA);
   constexpr int TILE_ROW_STEP = BQ * NCTA;
-
+  struct Item { int head, batch, row_base; };
+  // Walking the items without a division per item (decoding w = qt + n_qt * (head + H * batch) cost ~500 cycles at the top
+  // of every epilogue): the iterator keeps (qt, hb = head + H * batch) and advances by w_step.
+  struct ItemIter { int qt, hb; };
+  auto iter_first = [&]() {
+    ItemIter it;
+    it.qt = w0 % p.n_qt;
+    it.hb = w0 / p.n_qt;
+    return it;
+  };
+  auto iter_next = [&](ItemIter& it) {
+    it.qt += w_step;
+    if (it.qt >= p.n_qt) {
+      it.qt -= p.n_qt;
+      ++it.hb;
+      if (it.qt >= p.n_qt) {   // more than one (batch, head) per stride: few query tiles
+        it.hb += it.qt / p.n_qt;
+        it.qt %= p.n_qt;
+      }
+    }
+  };
+  // row_base: first query row of tile 0 of this CTA (a pair owns 2 * 256 rows, MMA tile t = rows [t * 256, +256) of them)
+  auto decode_item = [&](const ItemIter& it) {
+    Item wi;
+    if (it.hb < p.H) {
+      wi.head = it.hb;
+      wi.batch = 0;
+    } else {
+      wi.batch = it.hb / p.H;
+      wi.head = it.hb - wi.batch * p.H;
+    }
+    wi.row_base = it.qt * (2 * BQ * NCTA) + static_cast<int>(cta_rank) * BQ;
+    return wi;
+  };
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    if constexpr (STAGE) tma_prefetch_desc(&tmO);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_SLOTS; ++s) {
       mbar_init(&kv_full[s], 1);
@@ -206,6 +267,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&o_done[t], 1);
     }
     mbar_init(s_free, 4 * NCTA);
+    mbar_init(q_empty, 1);
+    mbar_init(&o_free[0], 4 * NCTA);
+    mbar_init(&o_free[1], 4 * NCTA);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -220,7 +284,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // Every role reads the TMEM base address from shared memory INSIDE its branch (read_tmem_base): read up here it was
+  // spilled across the role split and re-loaded from local memory inside the MMA issuer's loop; as a compile-time constant
+  // (the CTA allocates all 512 columns, the base can only be 0) ptxas materialised one uniform register per MMA.
+  auto read_tmem_base = [&]() {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(tmem_ptr)) : "memory");
+    return v;
+  };
 
   // Register budget per SMSP slot is 512 / 3 warps: give the two softmax warpgroups 208 registers each (a whole
   // 128-column S row lives in registers) and shrink the TMA/MMA warpgroup to 88.
@@ -236,10 +307,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // The peer may only refill a slot after the leader's MMAs of the previous round were committed (its own
         // kv_empty, multicast), i.e. after the leader's barrier finished that round, so its bytes can land before the
         // leader's expect_tx of the same round (the tx-count goes negative transiently, which is legal).
+        // (pairs are launched non-persistently: one work item)
+        const Item wi = decode_item(iter_first());
+        const int head = wi.head, batch = wi.batch;
         const uint32_t qbar = mapa_u32(q_full, 0);
         if (leader) mbar_arrive_expect_tx(q_full, 2 * 2 * TILE_BYTES);
         for (int t = 0; t < 2; ++t) {
-          const int row0 = row_base + t * TILE_ROW_STEP;
+          const int row0 = wi.row_base + t * TILE_ROW_STEP;
           tma_load_4d_2sm(q_smem + t * TILE_BYTES, &tmQ, qbar, 0, row0, head, batch);
           tma_load_4d_2sm(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, qbar, 64, row0, head, batch);
         }
@@ -270,33 +344,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (j + 2 < n_kv) load_k(j + 2);
         }
       } else {
-        mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
-        for (int t = 0; t < 2; ++t) {
-          const int row0 = row_base + t * TILE_ROW_STEP;
-          tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
-          tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
-        }
+        // The K/V ring runs on across work items: the next item's Q (once the last S MMA of this item has read the Q
+        // tiles: "Q empty") and its first K/V tiles are in flight while this item's last key tiles and epilogue run.
         int slot = 0;
         uint32_t phase = 0;
-        auto load_tile = [&](const CUtensorMap* tm, int j) {
-          role_wait(&kv_empty[slot], phase ^ 1);
-          uint8_t* dst = kv_smem + slot * KV_BYTES;
-          mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
-          tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV, head, batch);
-          tma_load_4d(dst + HALF_BYTES, tm, &kv_full[slot], 64, j * BKV, head, batch);
-          if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
-        };
-        if constexpr (PIPE == 1) {
-          load_tile(&tmK, 0);
-          if (n_kv > 1) load_tile(&tmK, 1);
-          for (int j = 0; j < n_kv; ++j) {
-            load_tile(&tmV, j);
-            if (j + 2 < n_kv) load_tile(&tmK, j + 2);
+        int n_it = 0;
+        for (ItemIter it = iter_first(); it.hb < p.n_hb; iter_next(it), ++n_it) {
+          if (!MULTI && n_it > 0) break;
+          const Item wi = decode_item(it);
+          const int head = wi.head, batch = wi.batch;
+          if (n_it > 0) role_wait(q_empty, (n_it - 1) & 1);
+          mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+          for (int t = 0; t < 2; ++t) {
+            const int row0 = wi.row_base + t * TILE_ROW_STEP;
+            tma_load_4d(q_smem + t * TILE_BYTES, &tmQ, q_full, 0, row0, head, batch);
+            tma_load_4d(q_smem + t * TILE_BYTES + HALF_BYTES, &tmQ, q_full, 64, row0, head, batch);
           }
-        } else {
-          for (int j = 0; j < n_kv; ++j) {
-            load_tile(&tmK, j);
-            load_tile(&tmV, j);
+          auto load_tile = [&](const CUtensorMap* tm, int j) {
+            role_wait(&kv_empty[slot], phase ^ 1);
+            uint8_t* dst = kv_smem + slot * KV_BYTES;
+            mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+            tma_load_4d(dst, tm, &kv_full[slot], 0, j * BKV, head, batch);
+            tma_load_4d(dst + HALF_BYTES, tm, &kv_full[slot], 64, j * BKV, head, batch);
+            if (++slot == KV_SLOTS) { slot = 0; phase ^= 1; }
+          };
+          if constexpr (PIPE == 1) {
+            load_tile(&tmK, 0);
+            if (n_kv > 1) load_tile(&tmK, 1);
+            for (int j = 0; j < n_kv; ++j) {
+              load_tile(&tmV, j);
+              if (j + 2 < n_kv) load_tile(&tmK, j + 2);
+            }
+          } else {
+            for (int j = 0; j < n_kv; ++j) {
+              load_tile(&tmK, j);
+              load_tile(&tmV, j);
+            }
           }
         }
       }
@@ -304,6 +387,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
    } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     if (leader && elect_one()) {
+      const uint32_t tmem_base = read_tmem_base();
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ * NCTA, BKV, 0);  // B = K tile, K-major
       constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ * NCTA, D, 1);    // B = V tile, MN-major
       const uint32_t q_addr = smem_u32(q_smem);
@@ -344,69 +428,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       //   PIPE 1:  K_0 K_1 V_0 K_2 V_1 K_3 ... V_{n-3} K_{n-1} V_{n-2} V_{n-1}: K runs TWO tiles ahead of V because S_t(j+2) is
       //            issued while V_j is in use and a 32 KB TMA load takes ~1000 cycles to land; item i + 5 reuses the slot of
       //            item i, so K_{j+2} waits for V_{j-2}'s release and V_j for K_{j-1}'s: >= 1.5 key tiles of lead each.
-      auto item_k = [&](int j) { return PIPE ? (j == 0 ? 0 : 2 * j - 1) : 2 * j; };
-      auto item_v = [&](int j) { return PIPE ? min(2 * j + 2, n_kv + j) : 2 * j + 1; };
+      uint32_t n_steps = 0;   // key-tile steps of the work items already done by this CTA: parity base of p_full / o_done
+      // PIPE 0 (one work item): ring item i lives in slot i % KV_SLOTS, phase (i / KV_SLOTS) & 1
       auto wait_item = [&](int item) {
         role_wait(&kv_full[item % KV_SLOTS], (item / KV_SLOTS) & 1);
         tc_fence_after();
       };
       auto release_item = [&](int item) { commit(&kv_empty[item % KV_SLOTS]); };
+      // PIPE 1: the MMA thread first touches the ring items in their LOAD order (K_0 K_1 V_0 K_2 V_1 K_3 ...), so one running
+      // (slot, phase) cursor replaces the item arithmetic (the % and / by 5 on a running item index cost ~80 instructions per
+      // key tile on the issuing thread -- the thread every hand-over waits for).
+      int ring_slot = 0;
+      uint32_t ring_phase = 0;
+      auto take = [&]() {   // wait for the next ring item to land; returns its slot
+        role_wait(&kv_full[ring_slot], ring_phase);
+        tc_fence_after();
+        const int sl = ring_slot;
+        if (++ring_slot == KV_SLOTS) { ring_slot = 0; ring_phase ^= 1; }
+        return sl;
+      };
+      auto release = [&](int sl) { commit(&kv_empty[sl]); };
       if constexpr (PIPE == 1) {
         // Issue order  S1(j+1) PV0(j) S0(j+2) PV1(j): an S only needs the shared S buffer back (the other tile's softmax has
         // pulled its row into registers), a PV only needs its P.  S_t(j+1) is therefore in TMEM long before softmax_t(j) ends.
-        // The c-th hand-back of the S buffer (S0(0), S1(0), S0(1), S1(1), ...) completes phase c of s_free.
+        // The c-th hand-back of the S buffer (S0(0), S1(0), S0(1), S1(1), ...) completes phase c of s_free; every S issue
+        // except the CTA's very first waits for the previous hand-back, also across work items.
         // (Two issuing threads -- one per stream -- were tried: the pipe interleaves their MMAs, an S group then takes ~1000
         // instead of ~600 cycles from issue to "S ready", and S is the stream on the critical path: 1195 vs 1330 TFLOP/s,
         // profiles/r02_attn_dual_issuer.log.)
+        // Persistent launch: work item i + 1 starts with S0(0) as soon as its Q and K_0 have landed -- under the epilogue of
+        // item i; only its first PV_t waits for that epilogue ("O free": the softmax warps have read O_t out of TMEM).
         uint32_t n_free = 0;
         auto wait_s_free = [&]() {
           role_wait(s_free, n_free & 1);
           ++n_free;
           tc_fence_after();
         };
-        role_wait(q_full, 0);
-        wait_item(item_k(0));
-        issue_s(0, item_k(0) % KV_SLOTS);
-        commit(&s_full[0]);
-        wait_s_free();
-        issue_s(1, item_k(0) % KV_SLOTS);
-        commit(&s_full[1]);
-        release_item(item_k(0));
-        if (n_kv > 1) {
-          wait_item(item_k(1));
-          wait_s_free();
-          issue_s(0, item_k(1) % KV_SLOTS);
+        const int n_my = !MULTI ? 1 : (w0 < p.n_items ? (p.n_items - w0 + w_step - 1) / w_step : 0);   // work items of this CTA
+#pragma unroll 1
+        for (int n_it = 0; n_it < n_my; ++n_it) {
+          const bool prof_cta = PROF && blockIdx.x == 0;
+          (void)prof_cta;
+          role_wait(q_full, n_it & 1);
+          ATTN_STAMP(0, 20);   // Q landed
+          const int k0 = take();                             // K_0
+          ATTN_STAMP(0, 21);   // K_0 landed
+          if (n_it > 0) wait_s_free();                       // softmax 1 pulled the previous item's last S1
+          issue_s(0, k0);
           commit(&s_full[0]);
-        }
-        for (int j = 0; j < n_kv; ++j) {
-          const int v_item = item_v(j);
-          if (j + 1 < n_kv) {
-            wait_s_free();                                   // softmax 0 pulled S0(j+1)
-            issue_s(1, item_k(j + 1) % KV_SLOTS);            // K_{j+1} landed before S0(j+1) was issued
-            commit(&s_full[1]);
-            release_item(item_k(j + 1));
-          }
-          ATTN_STAMP(j, 10);
-          wait_item(v_item);
-          issue_pv(0, v_item % KV_SLOTS, j == 0, j & 1);
-          ATTN_STAMP(j, 11);   // P0 seen ready, PV0 issued
-          commit(&o_done[0]);
-          if (j + 2 < n_kv) {
-            wait_item(item_k(j + 2));
-            ATTN_STAMP(j, 14);
-            wait_s_free();                                   // softmax 1 pulled S1(j+1)
-            ATTN_STAMP(j, 15);
-            issue_s(0, item_k(j + 2) % KV_SLOTS);
+          ATTN_STAMP(0, 22);   // S0(0) issued
+          wait_s_free();
+          issue_s(1, k0);
+          commit(&s_full[1]);
+          if (n_kv == 1) commit(q_empty);
+          release(k0);
+          int k_pend = 0;                                    // slot of K_{j+1}: S0(j+1) issued, S1(j+1) still to come
+          if (n_kv > 1) {
+            k_pend = take();                                 // K_1
+            wait_s_free();
+            issue_s(0, k_pend);
             commit(&s_full[0]);
           }
-          ATTN_STAMP(j, 12);
-          issue_pv(1, v_item % KV_SLOTS, j == 0, j & 1);
-          ATTN_STAMP(j, 13);   // P1 seen ready, PV1 issued
-          commit(&o_done[1]);
-          release_item(v_item);
+          for (int j = 0; j < n_kv; ++j) {
+            const uint32_t parity = ((MULTI ? n_steps : 0u) + j) & 1;
+            if (j + 1 < n_kv) {
+              wait_s_free();                                   // softmax 0 pulled S0(j+1)
+              issue_s(1, k_pend);                              // K_{j+1} landed before S0(j+1) was issued
+              commit(&s_full[1]);
+              if (j + 2 == n_kv) commit(q_empty);              // that was the item's last S MMA: the Q tiles may be refilled
+              release(k_pend);
+            }
+            ATTN_STAMP(j, 10);
+            const int v_slot = take();                         // V_j
+            if (j == 0 && n_it > 0) {
+              role_wait(&o_free[0], (n_it - 1) & 1);
+              tc_fence_after();
+            }
+            issue_pv(0, v_slot, j == 0, parity);
+            ATTN_STAMP(j, 11);   // P0 seen ready, PV0 issued
+            commit(&o_done[0]);
+            if (j + 2 < n_kv) {
+              k_pend = take();                                 // K_{j+2}
+              ATTN_STAMP(j, 14);
+              wait_s_free();                                   // softmax 1 pulled S1(j+1)
+              ATTN_STAMP(j, 15);
+              issue_s(0, k_pend);
+              commit(&s_full[0]);
+            }
+            ATTN_STAMP(j, 12);
+            if (j == 0 && n_it > 0) {
+              role_wait(&o_free[1], (n_it - 1) & 1);
+              tc_fence_after();
+            }
+            issue_pv(1, v_slot, j == 0, parity);
+            ATTN_STAMP(j, 13);   // P1 seen ready, PV1 issued
+            commit(&o_done[1]);
+            release(v_slot);
+          }
+          if constexpr (MULTI) n_steps += n_kv;
         }
       } else {
-        // round-1 order  PV0(j) S0(j+1) PV1(j) S1(j+1)  (P_t aliases S_t)
+        // round-1 order  PV0(j) S0(j+1) PV1(j) S1(j+1)  (P_t aliases S_t); launched non-persistently (one work item)
+        const bool prof_cta = PROF && blockIdx.x == 0;
+        (void)prof_cta;
         role_wait(q_full, 0);
         wait_item(0);
         issue_s(0, 0);
@@ -444,6 +568,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ softmax warps
     setmaxnreg_inc<REGS_SOFTMAX>();
+    const uint32_t tmem_base = read_tmem_base();
     const int t = warp >> 2;     // query tile
     const int quad = warp & 3;   // TMEM lane quadrant
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -453,13 +578,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t p_full_remote = NCTA == 2 ? mapa_u32(&p_full[t], 0) : 0u;
     const uint32_t s_free_remote = NCTA == 2 ? mapa_u32(s_free, 0) : 0u;
     const float sl2 = p.scale_log2;
+    const uint32_t o_free_remote = NCTA == 2 ? mapa_u32(&o_free[t], 0) : 0u;
+    uint32_t n_steps = 0;  // key-tile steps of the work items already done by this CTA: parity base of s_full / o_done
+    bool first_item = true;
+    for (ItemIter it = iter_first(); it.hb < p.n_hb; iter_next(it)) {
+    if (!MULTI && !first_item) break;   // one work item per CTA
+    first_item = false;
+    const uint32_t step_base = MULTI ? n_steps : 0u;
+    const bool prof_cta = PROF && blockIdx.x == 0;
+    (void)prof_cta;
     float m = -INFINITY;  // running max of s * scale_log2 actually used for P
     float l = 0.f;        // running sum of P
     // One key tile.  MASKED is a compile-time flag: only the LAST tile can be partial (Sk % 128 != 0); written as a run-time
     // `if` the compiler turned the masking into 128 ISETP + 128 SEL executed for EVERY tile -- 30 % of the loop's instructions.
     auto step = [&](const int j, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
-      mbar_wait(&s_full[t], j & 1);
+      const uint32_t parity = (step_base + j) & 1;
+      mbar_wait(&s_full[t], parity);
       tc_fence_after();
       if (quad == 0 && lane == 0) ATTN_STAMP(j, t * 5 + 0);
       const int valid = p.Sk - j * BKV;  // >= 128 except possibly for the last tile
@@ -504,7 +639,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else if (__any_sync(0xffffffffu, (m_new - m) > RESCALE_THRESHOLD)) {
         if constexpr (PIPE == 1) {
           // O_t is still being accumulated by PV_t(j-1) unless its "O done" phase has completed
-          mbar_wait(&o_done[t], (j - 1) & 1);
+          mbar_wait(&o_done[t], parity ^ 1);
           tc_fence_after();
           o_waited = true;
         }
@@ -553,7 +688,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if constexpr (PIPE == 1) {
         // P_t(j) goes where PV_t(j-1) reads P_t(j-1): that MMA must have completed (it long has, in steady state)
         if (j > 0 && !o_waited) {
-          mbar_wait(&o_done[t], (j - 1) & 1);
+          mbar_wait(&o_done[t], parity ^ 1);
           tc_fence_after();
         }
         tmem_st_x32(p_addr, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
@@ -573,22 +708,75 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < n_full; ++j) step(j, std::false_type{});
     if (n_full < n_kv) step(n_kv - 1, std::true_type{});
     // epilogue: O / l -> bf16 -> global
-    mbar_wait(&o_done[t], (n_kv - 1) & 1);
+    mbar_wait(&o_done[t], (step_base + n_kv - 1) & 1);
     tc_fence_after();
+    if (quad == 0 && lane == 0) ATTN_STAMP(n_kv - 1, 16 + 2 * t);   // last PV_t seen complete: epilogue begins
     const float inv_l = 1.0f / l;
-    const int row = row_base + t * TILE_ROW_STEP + quad * 32 + lane;
-    __nv_bfloat16* orow = p.o + batch * p.o_sb + head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
+    const Item wi = decode_item(it);
+    const int row = wi.row_base + t * TILE_ROW_STEP + quad * 32 + lane;
+    __nv_bfloat16* orow = p.o + wi.batch * p.o_sb + wi.head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
     if (p.n_peers > 0 && row < p.Sq) {
       const int d = row / p.rows_per_rank;
       orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
-             static_cast<int64_t>(head + p.head_off) * p.o_sh;
+             static_cast<int64_t>(wi.head + p.head_off) * p.o_sh;
     }
+    if constexpr (STAGE) {
+      // O_t rows [32 * quad, +32) of this warp: registers -> this warp's two 4 KB boxes (channels 0-63 and 64-127; 128-byte
+      // rows, 16-byte chunks XOR-swizzled by row & 7 = the tensor map's SWIZZLE_128B, conflict-free) -> ONE proxy fence and
+      // two bulk tensor stores of [32 rows x 64 channels]; rows >= Sq are clipped by the tensor map.  The whole row block has
+      // its own staging bytes, so nothing inside the epilogue waits for the TMA engine: the stores drain under the next
+      // work item, and the wait below (for the PREVIOUS item's stores) has long been satisfied.  (Smaller boxes that had to
+      // be re-used inside one epilogue cost a fence + store issue + drain wait per re-use: 2100-2700 cycles per item,
+      // profiles/r02_attn_cross_timeline.log.)
+      uint8_t* boxes = o_stage + (t * 4 + quad) * 8192;
+      const int row0 = wi.row_base + t * TILE_ROW_STEP + quad * 32;
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(o_addr + c * 32, r);
+        tmem_ld_wait();
+        if (c == 3) {
+          // O_t is in registers: the next work item's first PV_t may overwrite the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[t]);
+        }
+        uint8_t* box = boxes + (c >> 1) * 4096 + lane * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(box + (((q4 + 4 * (c & 1)) ^ (lane & 7)) << 4)) = o;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && row0 < p.Sq) {
+        tma_store_4d(&tmO, boxes, 0, row0, wi.head, wi.batch);
+        tma_store_4d(&tmO, boxes + 4096, 64, row0, wi.head, wi.batch);
+        tma_store_commit();
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t r[32];
       tmem_ld_x32(o_addr + c * 32, r);
       tmem_ld_wait();
-      if (row < p.Sq) {
+      if (c == 3) {
+        // O_t is in registers: the next work item's first PV_t may overwrite the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2 && !leader) mbar_arrive_release_cluster(o_free_remote);
+          else mbar_arrive(&o_free[t]);
+        }
+      }
+      if (row < p.Sq && !p.o_vec32) {
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint4 o;
@@ -598,7 +786,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
           reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
         }
+      } else if (row < p.Sq) {
+        // 32 bytes (a whole sector) per lane and instruction: STG.256 halves the line accesses of the 16-byte form
+#pragma unroll
+        for (int q8 = 0; q8 < 2; ++q8) {
+          uint32_t o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = pack_bf16x2(__uint_as_float(r[q8 * 16 + 2 * e]) * inv_l, __uint_as_float(r[q8 * 16 + 2 * e + 1]) * inv_l);
+          st_global_v8(orow + c * 32 + q8 * 16, o);
+        }
       }
+    }
+    }
+    if (quad == 0 && lane == 0) ATTN_STAMP(n_kv - 1, 17 + 2 * t);   // epilogue stores issued
+    if constexpr (MULTI) n_steps += n_kv;
+    }  // work items
+    if constexpr (STAGE) {
+      if (lane == 0) tma_store_wait<0>();   // bulk stores read shared memory: drain before the CTA exits
     }
   }
 
@@ -606,10 +811,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
+    const uint32_t tmem_base = read_tmem_base();
     if constexpr (NCTA == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
+#undef n_kv
+#undef w_step
 }  // namespace attn
 }  // namespace b200
 
@@ -661,33 +869,49 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   if (!q || !k || !v || !o) return B200_ERR_ARG;
   if (D != 128) return B200_ERR_SHAPE;
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return B200_ERR_SHAPE;
-  if (H > 65535 || B > 65535) return B200_ERR_SHAPE;
   if ((o_sb % 8) || (o_sh % 8) || (o_ss % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return B200_ERR_ALIGN;
 
   // B200_ATTN_2CTA=1 selects CTA pairs (0 / default: single CTAs); B200_ATTN_PIPE=0 selects the round-1 pipeline (1-CTA
   // only; the A/B partner), default the decoupled pipeline.  The opt-in to > 48 KB of dynamic shared memory is per device.
-  static int pair_mode = -2, pipe_mode = -2;
+  // B200_ATTN_PERSIST=0 launches one CTA per work item (the round-1 grid); default: one CTA per SM walks the items.
+  // B200_ATTN_STAGE_KV=n: key sequences of up to n tiles use the staged (TMA-store) epilogue with a 3-slot K/V ring (0 = never).
+  // B200_ATTN_MULTI_KV=n: key sequences of up to n tiles are launched persistently.
+  static int pair_mode = -2, pipe_mode = -2, persist_mode = -2, stage_kv = STAGE_MAX_KV_TILES, multi_kv = MULTI_MAX_KV_TILES;
   if (pair_mode == -2) {
-    const char* ev = getenv("B200_ATTN_2CTA");
-    pair_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
+    const char* ev = getenv("B200_ATTN_STAGE_KV");
+    if (ev) stage_kv = atoi(ev);
+    ev = getenv("B200_ATTN_MULTI_KV");
+    if (ev) multi_kv = atoi(ev);
+    ev = getenv("B200_ATTN_PERSIST");
+    persist_mode = ev ? (ev[0] == '0' ? 0 : 1) : 1;
     ev = getenv("B200_ATTN_PIPE");
     pipe_mode = ev ? (ev[0] == '0' ? 0 : 1) : 1;
+    ev = getenv("B200_ATTN_2CTA");
+    pair_mode = ev ? (ev[0] == '1' ? 1 : 0) : -1;
   }
   const bool use_pair = pipe_mode == 1 && (pair_mode == 1 || (pair_mode == -1 && PAIR_BY_DEFAULT && Sq > 2 * BQ));
   static std::atomic<bool> attr_done[kMaxDevices];
   if (!once_per_device(attr_done, [] {
         bool ok = true;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES) == cudaSuccess;
-        ok &= cudaFuncSetAttribute(attn_fwd_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES) == cudaSuccess;
+#define B200_ATTN_OPT_IN(NCTA, PIPE, STAGE, MULTI)                                                                        \
+  ok &= cudaFuncSetAttribute(attn_fwd_kernel<NCTA, PIPE, false, STAGE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             Cfg<NCTA, STAGE>::SMEM_BYTES) == cudaSuccess;                                                \
+  ok &= cudaFuncSetAttribute(attn_fwd_kernel<NCTA, PIPE, true, STAGE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             Cfg<NCTA, STAGE>::SMEM_BYTES) == cudaSuccess;
+        B200_ATTN_OPT_IN(1, 0, false, false)
+        B200_ATTN_OPT_IN(2, 1, false, false)
+        B200_ATTN_OPT_IN(1, 1, false, false)
+        B200_ATTN_OPT_IN(1, 1, false, true)
+        B200_ATTN_OPT_IN(1, 1, true, false)
+        B200_ATTN_OPT_IN(1, 1, true, true)
+#undef B200_ATTN_OPT_IN
         return ok;
       }))
     return B200_ERR_LAUNCH;
 
-  CUtensorMap tmQ, tmK, tmV;
+  const bool use_stage = pipe_mode == 1 && !use_pair && n_peers == 0 && (Sk + BKV - 1) / BKV <= stage_kv;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  const uint32_t box_o[4] = {64, 32, 1, 1};        // staged epilogue: one warp's 32 rows x 64 channels
   const uint32_t box[4] = {64, 128, 1, 1};
   const uint32_t box_k_pair[4] = {64, 64, 1, 1};   // pair: each CTA stages 64 of the 128 keys of a K tile
   {
@@ -708,6 +932,14 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     int rc = make_tmap_bf16(&tmV, v, 4, dims, str, box);
     if (rc) return rc;
   }
+  if (use_stage) {
+    uint64_t dims[4] = {128, (uint64_t)Sq, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {1, (uint64_t)o_ss, (uint64_t)o_sh, (uint64_t)o_sb};
+    int rc = make_tmap_bf16(&tmO, o, 4, dims, str, box_o);
+    if (rc) return rc;
+  } else {
+    tmO = tmQ;   // unused
+  }
   Params p;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -718,12 +950,23 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.head_off = head_off;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
   p.prof = prof;
+  p.prof_steps = prof_steps;
+  p.o_vec32 = !((o_sb % 16) || (o_sh % 16) || (o_ss % 16) || (reinterpret_cast<uintptr_t>(o) & 31));
+  for (int i = 0; i < n_peers; ++i)
+    if (reinterpret_cast<uintptr_t>(o_peers[i]) & 31) p.o_vec32 = 0;
+  const int rows_per_item = 2 * BQ * (use_pair ? 2 : 1);
+  const int64_t n_qt = (Sq + rows_per_item - 1) / rows_per_item;
+  const int64_t n_items = n_qt * H * B;
+  if (n_items > (1 << 30)) return B200_ERR_SHAPE;
+  p.n_kv = (Sk + BKV - 1) / BKV;
+  p.n_qt = static_cast<int>(n_qt);
+  p.n_hb = H * B;
+  p.n_items = static_cast<int>(n_items);
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use_pair) {
-    const int pairs = (Sq + 4 * BQ - 1) / (4 * BQ);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs, H, B);
+    cfg.gridDim = dim3(2 * p.n_items, 1, 1);
     cfg.blockDim = dim3(NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg<2>::SMEM_BYTES;
     cfg.stream = st;
@@ -734,21 +977,28 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1, true>, tmQ, tmK, tmV, p)
-                                : cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1>, tmQ, tmK, tmV, p);
+    const cudaError_t le = prof ? cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1, true>, tmQ, tmK, tmV, tmO, p)
+                                : cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, 1>, tmQ, tmK, tmV, tmO, p);
     if (le != cudaSuccess) {
       cudaGetLastError();
       return B200_ERR_LAUNCH;
     }
   } else {
-    dim3 grid((Sq + 2 * BQ - 1) / (2 * BQ), H, B);
-    if (pipe_mode == 1) {
-      if (prof) attn_fwd_kernel<1, 1, true><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-      else attn_fwd_kernel<1, 1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-    } else {
-      if (prof) attn_fwd_kernel<1, 0, true><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-      else attn_fwd_kernel<1, 0><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-    }
+    // persistent (decoupled pipeline only): one CTA per SM walks the work items -- for key sequences up to multi_kv tiles;
+    // beyond that the per-CTA prologue is amortised and the leaner single-item kernel is used.
+    const bool persist = pipe_mode == 1 && persist_mode == 1 && p.n_items > num_sms() && p.n_kv <= multi_kv;
+    dim3 grid(persist ? num_sms() : p.n_items, 1, 1);
+#define B200_ATTN_LAUNCH(PIPE, STAGE, MULTI)                                                                                        \
+  do {                                                                                                                             \
+    if (prof) attn_fwd_kernel<1, PIPE, true, STAGE, MULTI><<<grid, NUM_THREADS, Cfg<1, STAGE>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmO, p); \
+    else attn_fwd_kernel<1, PIPE, false, STAGE, MULTI><<<grid, NUM_THREADS, Cfg<1, STAGE>::SMEM_BYTES, st>>>(tmQ, tmK, tmV, tmO, p);     \
+  } while (0)
+    if (pipe_mode != 1) B200_ATTN_LAUNCH(0, false, false);
+    else if (use_stage && persist) B200_ATTN_LAUNCH(1, true, true);
+    else if (use_stage) B200_ATTN_LAUNCH(1, true, false);
+    else if (persist) B200_ATTN_LAUNCH(1, false, true);
+    else B200_ATTN_LAUNCH(1, false, false);
+#undef B200_ATTN_LAUNCH
   }
   B200_CHECK_LAUNCH();
   return B200_OK;

@@ -103,15 +103,16 @@ inline bool tmap_cache_lookup(const TmapKey& k, CUtensorMap* out, bool store) {
 }
 
 inline int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                                   const uint64_t* strides_elems, const uint32_t* box);
+                                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128);
 
+// swizzle_bytes: 128 (default; inner box extent <= 64 elements) or 64 (inner box extent <= 32 elements)
 inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_elems, const uint32_t* box) {
+                          const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.base = reinterpret_cast<uint64_t>(base);
   key.rank = static_cast<uint32_t>(rank);
-  key.swizzle = 128;
+  key.swizzle = static_cast<uint32_t>(swizzle_bytes);
   key.dev = static_cast<uint32_t>(current_device() + 1);
   for (int i = 0; i < rank; ++i) {
     key.dims[i] = dims[i];
@@ -119,15 +120,16 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     if (i > 0) key.strides[i - 1] = strides_elems[i];
   }
   if (tmap_cache_lookup(key, out, false)) return B200_OK;
-  const int rc = make_tmap_bf16_uncached(out, base, rank, dims, strides_elems, box);
+  const int rc = make_tmap_bf16_uncached(out, base, rank, dims, strides_elems, box, swizzle_bytes);
   if (rc == B200_OK) tmap_cache_lookup(key, out, true);
   return rc;
 }
 
 inline int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                                   const uint64_t* strides_elems, const uint32_t* box) {
+                                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return B200_ERR_DRIVER;
+  if (swizzle_bytes != 128 && swizzle_bytes != 64) return B200_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return B200_ERR_ALIGN;
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -143,7 +145,8 @@ inline int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank,
     }
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[apex_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);

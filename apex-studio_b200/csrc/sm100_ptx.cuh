@@ -376,6 +376,12 @@ B200_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// 32-byte global store (STG.256, sm_100+): one full sector per lane.  `p` must be 32-byte aligned.
+B200_DEVICE void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 B200_DEVICE float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 B200_DEVICE float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 B200_DEVICE float fast_exp2(float x) {

@@ -32,7 +32,8 @@ def timed(fn, iters):
 
 def main():
     res = {"variant": os.environ.get("B200_ATTN_VARIANT", "default"), "pair": os.environ.get("B200_ATTN_2CTA", "default")}
-    for (B, H, Sq, Sk) in [(1, 2, 300, 333), (2, 3, 1000, 777), (1, 32, 1024, 1024), (1, 4, 2048, 512), (1, 2, 128, 64), (1, 1, 4000, 4100)]:
+    for (B, H, Sq, Sk) in [(1, 2, 300, 333), (2, 3, 1000, 777), (1, 32, 1024, 1024), (1, 4, 2048, 512), (1, 2, 128, 64), (1, 1, 4000, 4100),
+                            (1, 40, 2300, 333), (2, 24, 1500, 130)]:   # > 148 work items: the persistent grid
         torch.manual_seed(42)
         q, k, v = (torch.randn(B, H, s, 128, device="cuda", dtype=torch.bfloat16) for s in (Sq, Sk, Sk))
         out = ops.attention(q, k, v)
@@ -46,10 +47,13 @@ def main():
         torch.cuda.synchronize()
         ref = sdpa(q[:, :2], k[:, :2], v[:, :2])
         res["rel_full_2heads_vs_sdpa"] = round(rel(out[:, :2], ref), 5)
-        for name, hs, sk, iters in (("self40", 40, 75600, 8), ("self2", 2, 75600, 20), ("cross40", 40, 512, 50)):
-            qq, kk, vv = q[:, :hs], k[:, :hs, :sk], v[:, :hs, :sk]
+        # flux / qwen: the joint self-attention of FLUX.1-dev 1024^2 (24 heads x 4608) and QwenImage-Edit (24 x 8704)
+        for name, hs, sq, sk, iters in (("self40", 40, 75600, 75600, 8), ("self2", 2, 75600, 75600, 20),
+                                        ("cross40", 40, 75600, 512, 50), ("flux24", 24, 4608, 4608, 50),
+                                        ("qwen24", 24, 8704, 8704, 50)):
+            qq, kk, vv = q[:, :hs, :sq], k[:, :hs, :sk], v[:, :hs, :sk]
             oo = torch.empty_like(qq)
-            flop = 4.0 * hs * 75600 * sk * 128
+            flop = 4.0 * hs * sq * sk * 128
             ms = timed(lambda: ops.attention(qq, kk, vv, out=oo), iters)
             ms_ref = timed(lambda: sdpa(qq, kk, vv), iters)
             res[name] = {"ms": round(ms, 3), "tflops": round(flop / ms / 1e9, 1), "sdpa_ms": round(ms_ref, 3),

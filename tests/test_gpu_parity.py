@@ -76,7 +76,10 @@ def test_attention_reference_recipe(ops):
 
 
 @pytest.mark.parametrize("B,H,Sq,Sk", [(1, 1, 1, 1), (1, 2, 7, 300), (2, 3, 300, 77), (1, 2, 129, 255), (1, 1, 513, 640),
-                                       (1, 4, 1024, 512), (1, 2, 2000, 3000)])
+                                       (1, 4, 1024, 512), (1, 2, 2000, 3000),
+                                       # > 148 work items: the persistent grid (one CTA per SM walks 2-8 items each; 1, 3
+                                       # and 5 key tiles per item, ragged query and key tails, items crossing heads / batches)
+                                       (1, 40, 2300, 100), (2, 24, 1500, 333), (1, 40, 4096, 512), (3, 7, 3000, 640)])
 def test_attention_ragged_shapes(ops, B, H, Sq, Sk):
     torch.manual_seed(Sq * 1000 + Sk)
     q = torch.randn(B, H, Sq, 128, device=DEV, dtype=torch.bfloat16)

@@ -44,12 +44,13 @@ def _run(cmd, env):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("env", [{"B200_ATTN_PIPE": "0"}, {"B200_ATTN_2CTA": "1"}, {"B200_ATTN_PIPE": "1", "B200_ATTN_2CTA": "0"}])
+@pytest.mark.parametrize("env", [{"B200_ATTN_PIPE": "0"}, {"B200_ATTN_2CTA": "1"}, {"B200_ATTN_PIPE": "1", "B200_ATTN_2CTA": "0"},
+                                 {"B200_ATTN_PERSIST": "0"}])
 def test_attention_form_in_subprocess(env):
     res = _run([sys.executable, os.path.join(ROOT, "scripts", "attn_variant_ab.py")], env)
     assert res["nan"] is False
     errs = {k: v for k, v in res.items() if k.startswith("rel_")}
-    assert len(errs) == 6 and all(v <= 5e-3 for v in errs.values()), errs
+    assert len(errs) == 8 and all(v <= 5e-3 for v in errs.values()), errs
 
 
 @pytest.mark.parametrize("env", [{"B200_LINEAR_2CTA": "0"}, {"B200_LINEAR_2CTA": "1"}, {"B200_LINEAR_SMALLM": "1"},
