@@ -382,6 +382,13 @@ B200_DEVICE void st_global_v8(void* p, const uint32_t (&v)[8]) {
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 32-byte global load (LDG.256, sm_100+).  `p` must be 32-byte aligned.
+B200_DEVICE void ld_global_v8(const void* p, uint4 (&v)[2]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0].x), "=r"(v[0].y), "=r"(v[0].z), "=r"(v[0].w), "=r"(v[1].x), "=r"(v[1].y), "=r"(v[1].z), "=r"(v[1].w)
+               : "l"(p)
+               : "memory");
+}
 B200_DEVICE float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 B200_DEVICE float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 B200_DEVICE float fast_exp2(float x) {
