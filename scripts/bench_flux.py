@@ -93,7 +93,11 @@ def main():
     prof = os.environ.get("B200_PROFILE") == "1"    # ncu --profile-from-start off: capture the timed steps only
     if prof:
         torch.cuda.cudart().cudaProfilerStart()
+    from bench import ClockSampler   # nvidia-smi clocks / throttle reasons sampled during the timed region
+    clk = ClockSampler(0)
+    clk.start()
     ms = timed(resident, a.steps)
+    clocks = clk.stop()
     if prof:
         torch.cuda.cudart().cudaProfilerStop()
     launches = ops.launch_count // a.steps
@@ -115,7 +119,7 @@ def main():
            "1 forward + flow-match Euler per step", "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": a.steps,
            "warmup": a.warmup, "dtype": "bf16", "data": "synthetic", "layers": [a.layers, a.single_layers],
            "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / peak, "peak": peak,
-           "gpu_launches_per_step": launches,
+           "gpu_launches_per_step": launches, "clocks": clocks,
            "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": (lat_h.numel() + enc_h.numel() + pooled_h.numel()) * 2, "d2h_bytes_per_step": out_h.numel() * 2},
            "seconds_per_image_28_steps": 28 * ms / 1000.0, "parameter_gb": m.parameter_bytes() / 1e9}

@@ -67,15 +67,19 @@ def main():
     y = steps(0, a.warmup)
     ops.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from bench import ClockSampler   # nvidia-smi clocks / throttle reasons sampled during the timed region (rank 0's GPU)
+    clk = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clk.start()
     e0.record()
     y = steps(a.warmup, a.steps)
     e1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    clocks = clk.stop()
     ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -89,7 +93,7 @@ def main():
                           "tokens, d=2048, 16 heads, %d dual-stream blocks), CFG on: 2 forwards + combine + Euler per step" % a.layers,
                           "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "n_gpus": world,
                           "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}", "steps": a.steps, "warmup": a.warmup, "dtype": "bf16",
-                          "data": "synthetic", "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9,
+                          "data": "synthetic", "clocks": clocks, "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9,
                           "tflops_per_gpu": fl / ms / 1e9 / world, "frac_of_peak_per_gpu": fl / ms / 1e9 / world / peak, "peak": peak,
                           "gpu_launches_per_step_rank0": ops.launch_count // a.steps, "finite": bool(torch.isfinite(y).all()),
                           "parameter_gb": m.parameter_bytes() / 1e9}), flush=True)

@@ -43,6 +43,9 @@ def main():
     for _ in range(a.warmup):
         y = fwd()
     ops.launch_count = 0
+    from bench import ClockSampler   # nvidia-smi clocks / throttle reasons sampled during the timed region
+    clk = ClockSampler(0)
+    clk.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -50,6 +53,7 @@ def main():
         y = fwd()
     e1.record()
     torch.cuda.synchronize()
+    clocks = clk.stop()
     ms = e0.elapsed_time(e1) / a.steps
     S = n_img + n_txt
     fl = a.layers * (24.0 * S * d * d + 4.0 * S * S * d)
@@ -60,7 +64,7 @@ def main():
                       "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "seconds_per_image_8_steps": 8 * ms / 1000.0,
                       "steps": a.steps, "warmup": a.warmup, "dtype": "bf16", "data": "synthetic",
                       "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9, "frac_of_peak": fl / ms / 1e9 / peak, "peak": peak,
-                      "gpu_launches_per_step": ops.launch_count // a.steps, "finite": bool(torch.isfinite(y).all()),
+                      "gpu_launches_per_step": ops.launch_count // a.steps, "clocks": clocks, "finite": bool(torch.isfinite(y).all()),
                       "parameter_gb": m.parameter_bytes() / 1e9}))
 
 
