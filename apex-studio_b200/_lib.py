@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200_cfg_combine": (_i, [_p, _p, _p, _f, _i64, _p]),
     "b200_rmsnorm_rope_scatter": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _i, _i64, _i, _p]),
     "b200_attn_fwd_scatter": (_i, [_p, _p, _p, _i, _i, _i, _i] + [_i64] * 6 + [_p, _i, _i, _i, _i64, _i64, _f, _p]),
+    "b200_attn_fwd_scatter_joint": (_i, [_p, _p, _p, _i, _i, _i, _i] + [_i64] * 6 + [_p, _i, _i, _i, _i64, _i64, _i, _i, _f, _p]),
     "b200_conv3d_cl": (_i, [_p, _p, _p, _p, _p] + [_i] * 13 + [_p]),
     "b200_rmsnorm_silu_cl": (_i, [_p, _p, _p, _i64, _i, _i, _p]),
     "b200_upsample2x_cl": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -106,6 +106,10 @@ struct Params {
   int n_peers;        // 0 = plain store into `o`
   int rows_per_rank;  // S / P
   int head_off;       // first global head computed by this rank
+  // Joint (dual-stream) sequences: `rep_rows` query rows -- the replicated text stream -- are stored to EVERY peer; the other
+  // rows are token-sharded as above.  rep_first: the replicated rows come first (Flux / QwenImage), else last (HunyuanVideo-1.5).
+  // Every peer's buffer is laid out like its local joint sequence: [rep_rows + rows_per_rank, H_total * 128] in the same order.
+  int rep_rows, rep_first;
   long long* prof;    // PROF kernels only: [steps][16] SM-clock timestamps of CTA (0,0,0) (b200_attn_fwd_prof)
   int prof_steps;
 };
@@ -715,10 +719,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const Item wi = decode_item(it);
     const int row = wi.row_base + t * TILE_ROW_STEP + quad * 32 + lane;
     __nv_bfloat16* orow = p.o + wi.batch * p.o_sb + wi.head * p.o_sh + static_cast<int64_t>(row) * p.o_ss;
+    int n_dst = 1;               // peers this row is stored to (replicated text rows of a joint sequence: all of them)
+    int64_t peer_row_off = 0;    // element offset of the row inside a peer's buffer
     if (p.n_peers > 0 && row < p.Sq) {
-      const int d = row / p.rows_per_rank;
-      orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(row - d * p.rows_per_rank) * p.o_ss +
-             static_cast<int64_t>(wi.head + p.head_off) * p.o_sh;
+      const int n_shard = p.Sq - p.rep_rows;
+      const int rs = p.rep_first ? row - p.rep_rows : row;   // index among the token-sharded rows (if it is one)
+      if (rs >= 0 && rs < n_shard) {
+        const int d = rs / p.rows_per_rank;
+        const int local = rs - d * p.rows_per_rank + (p.rep_first ? p.rep_rows : 0);
+        orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[d]) + static_cast<int64_t>(local) * p.o_ss +
+               static_cast<int64_t>(wi.head + p.head_off) * p.o_sh;
+      } else {
+        const int local = p.rep_first ? row : p.rows_per_rank + (row - n_shard);
+        peer_row_off = static_cast<int64_t>(local) * p.o_ss + static_cast<int64_t>(wi.head + p.head_off) * p.o_sh;
+        orow = reinterpret_cast<__nv_bfloat16*>(p.o_peer[0]) + peer_row_off;
+        n_dst = p.n_peers;
+      }
     }
     if constexpr (STAGE) {
       // O_t rows [32 * quad, +32) of this warp: registers -> this warp's two 4 KB boxes (channels 0-63 and 64-127; 128-byte
@@ -776,25 +792,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           else mbar_arrive(&o_free[t]);
         }
       }
-      if (row < p.Sq && !p.o_vec32) {
+      if (row < p.Sq) {
+        uint32_t pk8[16];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]) * inv_l, __uint_as_float(r[q4 * 8 + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]) * inv_l, __uint_as_float(r[q4 * 8 + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]) * inv_l, __uint_as_float(r[q4 * 8 + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]) * inv_l, __uint_as_float(r[q4 * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[q4] = o;
-        }
-      } else if (row < p.Sq) {
-        // 32 bytes (a whole sector) per lane and instruction: STG.256 halves the line accesses of the 16-byte form
+        for (int e = 0; e < 16; ++e)
+          pk8[e] = pack_bf16x2(__uint_as_float(r[2 * e]) * inv_l, __uint_as_float(r[2 * e + 1]) * inv_l);
+        for (int dst = 0; dst < n_dst; ++dst) {
+          __nv_bfloat16* od = dst == 0 ? orow : reinterpret_cast<__nv_bfloat16*>(p.o_peer[dst]) + peer_row_off;
+          if (p.o_vec32) {
+            // 32 bytes (a whole sector) per lane and instruction: STG.256 halves the line accesses of the 16-byte form
+            st_global_v8(od + c * 32, *reinterpret_cast<uint32_t(*)[8]>(&pk8[0]));
+            st_global_v8(od + c * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&pk8[8]));
+          } else {
 #pragma unroll
-        for (int q8 = 0; q8 < 2; ++q8) {
-          uint32_t o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o[e] = pack_bf16x2(__uint_as_float(r[q8 * 16 + 2 * e]) * inv_l, __uint_as_float(r[q8 * 16 + 2 * e + 1]) * inv_l);
-          st_global_v8(orow + c * 32 + q8 * 16, o);
+            for (int q4 = 0; q4 < 4; ++q4)
+              reinterpret_cast<uint4*>(od + c * 32)[q4] = make_uint4(pk8[q4 * 4], pk8[q4 * 4 + 1], pk8[q4 * 4 + 2], pk8[q4 * 4 + 3]);
+          }
         }
       }
     }
@@ -825,7 +838,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                          float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
-                         long long* prof = nullptr, int prof_steps = 0);
+                         long long* prof = nullptr, int prof_steps = 0, int rep_rows = 0, int rep_first = 0);
 
 // Diagnostics: b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA (0,0,0) written to
 // prof[prof_steps][32] (device memory): columns 0-4 softmax tile 0 (S seen ready, S in registers, row max done, P stores
@@ -847,23 +860,31 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
                        scale, nullptr, 0, 0, 0, stream);
 }
 
+extern "C" int b200_attn_fwd_scatter_joint(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D,
+                                           int64_t q_sh, int64_t q_ss, int64_t k_sh, int64_t k_ss, int64_t v_sh, int64_t v_ss,
+                                           void* const* o_peers, int n_peers, int rows_per_rank, int head_off, int64_t o_sh,
+                                           int64_t o_ss, int rep_rows, int rep_first, float scale, void* stream) {
+  if (!o_peers || n_peers < 1 || n_peers > 8 || rows_per_rank <= 0 || rep_rows < 0 || rep_rows > Sq) return B200_ERR_ARG;
+  if (static_cast<int64_t>(rows_per_rank) * n_peers < Sq - rep_rows) return B200_ERR_SHAPE;
+  for (int i = 0; i < n_peers; ++i)
+    if (!o_peers[i] || (reinterpret_cast<uintptr_t>(o_peers[i]) & 15)) return B200_ERR_ALIGN;
+  return attn_fwd_impl(q, k, v, o_peers[0], 1, H, Sq, Sk, D, 0, q_sh, q_ss, 0, k_sh, k_ss, 0, v_sh, v_ss, 0, o_sh, o_ss,
+                       scale, o_peers, n_peers, rows_per_rank, head_off, stream, nullptr, 0, rep_rows, rep_first ? 1 : 0);
+}
+
 extern "C" int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D,
                                      int64_t q_sh, int64_t q_ss, int64_t k_sh, int64_t k_ss, int64_t v_sh, int64_t v_ss,
                                      void* const* o_peers, int n_peers, int rows_per_rank, int head_off, int64_t o_sh,
                                      int64_t o_ss, float scale, void* stream) {
-  if (!o_peers || n_peers < 1 || n_peers > 8 || rows_per_rank <= 0) return B200_ERR_ARG;
-  if (static_cast<int64_t>(rows_per_rank) * n_peers < Sq) return B200_ERR_SHAPE;
-  for (int i = 0; i < n_peers; ++i)
-    if (!o_peers[i] || (reinterpret_cast<uintptr_t>(o_peers[i]) & 15)) return B200_ERR_ALIGN;
-  return attn_fwd_impl(q, k, v, o_peers[0], 1, H, Sq, Sk, D, 0, q_sh, q_ss, 0, k_sh, k_ss, 0, v_sh, v_ss, 0, o_sh, o_ss,
-                       scale, o_peers, n_peers, rows_per_rank, head_off, stream);
+  return b200_attn_fwd_scatter_joint(q, k, v, H, Sq, Sk, D, q_sh, q_ss, k_sh, k_ss, v_sh, v_ss, o_peers, n_peers, rows_per_rank,
+                                     head_off, o_sh, o_ss, 0, 0, scale, stream);
 }
 
 static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                          float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
-                         long long* prof, int prof_steps) {
+                         long long* prof, int prof_steps, int rep_rows, int rep_first) {
   using namespace b200;
   using namespace b200::attn;
   if (!q || !k || !v || !o) return B200_ERR_ARG;
@@ -948,6 +969,8 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.n_peers = n_peers;
   p.rows_per_rank = rows_per_rank;
   p.head_off = head_off;
+  p.rep_rows = rep_rows;
+  p.rep_first = rep_first;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
   p.prof = prof;
   p.prof_steps = prof_steps;

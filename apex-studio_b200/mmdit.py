@@ -69,7 +69,29 @@ def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: S
         ops.adaln_zero_modulate(ws.h[s.rows], scale_msa, shift_msa, eps=eps, out=ws.norm[s.rows])
         ops.linear(ws.norm[s.rows], w[s.qkv + ".weight"], w.get(s.qkv + ".bias"), out=ws.qkv[s.rows])
         ops.headnorm_rope_(ws.qkv[s.rows, :d], ws.qkv[s.rows, d:2 * d], w[s.norm_q], w[s.norm_k], s.rope, heads, eps, norm_mode)
-    if par is not None and par.sp_size > 1:
+    attn = ws.attn
+    if par is not None and par.sp_size > 1 and par.use_p2p:
+        # Ulysses exchange fused into the kernels over NVLink peer memory (parallel.JointPeerExchange).  Buffer reuse across
+        # blocks is ordered by the two barriers exactly as in the Wan path (wan/model.py::block): no rank scatters block
+        # L+1's q/k/v into a plane before every rank has finished attention L (barrier 1), and no attention L+1 stores into
+        # an `o` buffer before its owner has issued the out-projections of block L (they precede its barrier 0 in stream order).
+        img, txt = streams[0], streams[1]
+        img_first = (img.rows.start or 0) == 0
+        n_txt = ws.qkv[txt.rows].shape[0]
+        ex = par.joint_peer_exchange(n_img_total, n_txt, heads, 128, img_first, ws.qkv.device)
+        for which in range(3):
+            ops.rmsnorm_rope_scatter(ws.qkv[img.rows, which * d:(which + 1) * d], None, None, heads, eps, ex.qkv_peers, ex.P,
+                                     which * ex.plane + ex.img_off * ex.width, ex.row0, norm=False)
+            ex.qkv[which, ex.txt_off:ex.txt_off + n_txt].copy_(
+                ws.qkv[txt.rows, which * d + ex.group_col0:which * d + ex.group_col0 + ex.width])
+        ex.barrier(0)
+        hp = heads // par.sp_size
+        as4 = lambda t: t.view(1, ex.S, hp, 128).transpose(1, 2)
+        ops.attention_scatter(as4(ex.qkv[0]), as4(ex.qkv[1]), as4(ex.qkv[2]), ex.o_peers, ex.P, ex.n_local, ex.head_off, d,
+                              rep_rows=n_txt, rep_first=not img_first)
+        ex.barrier(1)
+        attn = ex.o      # [n_txt + n_img_local, d] in the local joint order == the row ranges of ws.attn
+    elif par is not None and par.sp_size > 1:
         img, txt = streams[0], streams[1]
         img_first = (img.rows.start or 0) == 0
         qkv_h = par.joint_tokens_to_heads(ws.qkv, img.rows, txt.rows, heads, 128, img_first)   # [3, S_joint, (H/P)*128]
@@ -85,7 +107,7 @@ def dual_stream_block(w: Dict[str, torch.Tensor], ws: JointWorkspace, streams: S
     for s in streams:
         gate_msa, shift_mlp, scale_mlp, gate_mlp = s.mod[2], s.mod[3], s.mod[4], s.mod[5]
         h = ws.h[s.rows]
-        ops.linear(ws.attn[s.rows], w[s.out + ".weight"], w.get(s.out + ".bias"), epilogue=ops.EPI_GATE_RES, out=h,
+        ops.linear(attn[s.rows], w[s.out + ".weight"], w.get(s.out + ".bias"), epilogue=ops.EPI_GATE_RES, out=h,
                    gate=gate_msa)
         ops.adaln_zero_modulate(h, scale_mlp, shift_mlp, eps=eps, out=ws.norm[s.rows])
         if s.swiglu:

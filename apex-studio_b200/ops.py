@@ -259,9 +259,12 @@ def rmsnorm_rope_scatter(x: torch.Tensor, weight: Optional[torch.Tensor], rope: 
 
 
 def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_peers, n_peers: int, rows_per_rank: int,
-                      head_off: int, o_row_stride: int, softmax_scale: Optional[float] = None) -> None:
+                      head_off: int, o_row_stride: int, softmax_scale: Optional[float] = None, *, rep_rows: int = 0,
+                      rep_first: bool = False) -> None:
     """attention for q/k/v [1,H,S,128] whose output rows are stored into the token-owning peers' [S/P, H_total*128]
-    buffers (heads -> tokens exchange fused into the attention epilogue)."""
+    buffers (heads -> tokens exchange fused into the attention epilogue).  Joint sequences of the dual-stream families:
+    ``rep_rows`` rows (the replicated text stream; first if ``rep_first`` else last) are stored to every peer, whose buffer
+    is [rep_rows + S_img/P, H_total*128] in its local joint order."""
     for name, t in (("q", q), ("k", k), ("v", v)):
         _require_cuda_bf16(name, t)
         if t.dim() != 4 or t.stride(3) != 1 or any(st % 8 for st in t.stride()[:3]) or t.data_ptr() % 16:
@@ -275,10 +278,10 @@ def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_peers
         raise ValueError(f"shape mismatch: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)}")
     scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
     lib = _lib.load()
-    rc = lib.b200_attn_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), H, Sq, Sk, D, q.stride(1), q.stride(2),
-                                   k.stride(1), k.stride(2), v.stride(1), v.stride(2), o_peers, n_peers, rows_per_rank,
-                                   head_off, D, o_row_stride, scale, _stream())
-    _lib.check(rc, "b200_attn_fwd_scatter")
+    rc = lib.b200_attn_fwd_scatter_joint(q.data_ptr(), k.data_ptr(), v.data_ptr(), H, Sq, Sk, D, q.stride(1), q.stride(2),
+                                         k.stride(1), k.stride(2), v.stride(1), v.stride(2), o_peers, n_peers, rows_per_rank,
+                                         head_off, D, o_row_stride, int(rep_rows), 1 if rep_first else 0, scale, _stream())
+    _lib.check(rc, "b200_attn_fwd_scatter_joint")
     _count()
 
 

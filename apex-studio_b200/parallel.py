@@ -50,6 +50,16 @@ class ParallelContext:
             self._p2p[key] = PeerExchange(self, tokens_total, heads, head_dim, device)
         return self._p2p[key]
 
+    def joint_peer_exchange(self, n_img_total: int, n_txt: int, heads: int, head_dim: int, img_first: bool,
+                            device) -> "JointPeerExchange":
+        """Symmetric buffers of the dual-stream (joint sequence) exchange for one shape; collective on first use."""
+        if self._p2p is None:
+            self._p2p = {}
+        key = ("joint", n_img_total, n_txt, heads, head_dim, img_first)
+        if key not in self._p2p:
+            self._p2p[key] = JointPeerExchange(self, n_img_total, n_txt, heads, head_dim, img_first, device)
+        return self._p2p[key]
+
     # ------------------------------------------------------------------------------------ construction
     @classmethod
     def single(cls) -> "ParallelContext":
@@ -207,6 +217,49 @@ class PeerExchange:
         self.row0 = par.sp_rank * self.n_local
         self.qkv = symm_mem.empty((3, tokens_total, self.width), dtype=torch.bfloat16, device=device)
         self.o = symm_mem.empty((self.n_local, heads * head_dim), dtype=torch.bfloat16, device=device)
+        self.h_qkv = symm_mem.rendezvous(self.qkv, par.sp_group)
+        self.h_o = symm_mem.rendezvous(self.o, par.sp_group)
+        self.qkv_peers = (ctypes.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])
+        self.o_peers = (ctypes.c_void_p * P)(*[int(p) for p in self.h_o.buffer_ptrs])
+
+    def barrier(self, channel: int) -> None:
+        """Device-side barrier over the sp group on the current stream (all earlier peer stores are visible after it)."""
+        self.h_qkv.barrier(channel=channel)
+
+
+class JointPeerExchange:
+    """PeerExchange for the JOINT sequences of the dual-stream families (``mmdit.dual_stream_block``): the image / latent
+    stream is token-sharded, the short text stream is replicated on every rank.
+
+    * ``qkv`` [3, S_img + n_txt, (H/P)*Dh] -- receive planes of MY head group over the whole joint sequence, in the
+      reference's concatenation order: every rank stores the q / k / v rows of its image shard straight into the owners'
+      planes over NVLink (``b200_rmsnorm_rope_scatter`` in its pure scatter form, after the in-place per-head norm +
+      RoPE), the text rows are a local column slice (the text q|k|v of all heads were computed here).
+    * ``o`` [n_txt + S_img/P, H*Dh] in MY local joint order -- the attention epilogue of every rank stores the image rows
+      of its head group to the token owner and the text rows to EVERY rank (``b200_attn_fwd_scatter_joint``), so the
+      replicated text stream continues without the NCCL all-gather of the baseline path.
+    Replaces, per block: pack copy + ``all_to_all_single`` + permute + ``cat`` (tokens -> heads) and ``all_to_all_single`` +
+    ``all_gather`` + copy (heads -> tokens).  Two device-side barriers per block, as in the Wan path."""
+
+    def __init__(self, par: "ParallelContext", n_img_total: int, n_txt: int, heads: int, head_dim: int, img_first: bool,
+                 device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        P = par.sp_size
+        if heads % P or n_img_total % P:
+            raise ValueError("heads and image tokens must be divisible by the sequence-parallel size")
+        self.P, self.width, self.n_local, self.n_txt = P, (heads // P) * head_dim, n_img_total // P, n_txt
+        self.n_img_total, self.img_first, self.S = n_img_total, img_first, n_img_total + n_txt
+        self.plane = self.S * self.width
+        self.head_off = par.sp_rank * (heads // P)
+        self.group_col0 = par.sp_rank * self.width        # my head group's first column inside a [*, H*Dh] block
+        self.row0 = par.sp_rank * self.n_local            # my shard's first image row
+        self.img_off = 0 if img_first else n_txt          # first image row inside the joint sequence
+        self.txt_off = n_img_total if img_first else 0
+        self.qkv = symm_mem.empty((3, self.S, self.width), dtype=torch.bfloat16, device=device)
+        self.o = symm_mem.empty((self.n_local + n_txt, heads * head_dim), dtype=torch.bfloat16, device=device)
         self.h_qkv = symm_mem.rendezvous(self.qkv, par.sp_group)
         self.h_o = symm_mem.rendezvous(self.o, par.sp_group)
         self.qkv_peers = (ctypes.c_void_p * P)(*[int(p) for p in self.h_qkv.buffer_ptrs])

@@ -151,6 +151,17 @@ int b200_attn_fwd_scatter(const void* q, const void* k, const void* v, int H, in
                           void* stream);
 
 /*
+ * The same for the JOINT sequences of the dual-stream families (hunyuanvideo15/base/model.py:617-694 concatenates latent and
+ * text tokens before the attention call; flux/base/attention.py and qwenimage/base/model.py put the text first): Sq - rep_rows
+ * rows are token-sharded as above, `rep_rows` rows -- the replicated text stream, first (rep_first != 0) or last -- are written
+ * to EVERY peer.  Each peer's buffer is [rep_rows + rows_per_rank, H_total * 128] in its local joint order.
+ */
+int b200_attn_fwd_scatter_joint(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D, int64_t q_sh,
+                                int64_t q_ss, int64_t k_sh, int64_t k_ss, int64_t v_sh, int64_t v_ss, void* const* o_peers,
+                                int n_peers, int rows_per_rank, int head_off, int64_t o_sh, int64_t o_ss, int rep_rows,
+                                int rep_first, float scale, void* stream);
+
+/*
  * Diagnostics (not a reference call site): b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA
  * (0,0,0) written to prof[prof_steps][32] (int64, device memory): columns 0-4 softmax of query tile 0 (S seen ready,
  * S in registers, row max done, P stores issued, "P ready" signalled), 5-9 the same for tile 1, 10-13 the MMA thread

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--layers", type=int, default=54)
+    ap.add_argument("--p2p", action="store_true", help="fused NVLink peer-memory exchange (parallel.JointPeerExchange) instead of NCCL")
     a = ap.parse_args()
     from apex_studio_b200 import denoise, ops
     from apex_studio_b200.hunyuanvideo15 import HunyuanVideo15Config, HunyuanVideo15Transformer3DModel
@@ -40,7 +41,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    par = ParallelContext.create(use_cfg=True) if world > 1 else ParallelContext.single()
+    par = ParallelContext.create(use_cfg=True, use_p2p=a.p2p) if world > 1 else ParallelContext.single()
     m = HunyuanVideo15Transformer3DModel(HunyuanVideo15Config(num_layers=a.layers)).init_random_weights(dev)
     g = torch.Generator(device=dev).manual_seed(42)
     bf = torch.bfloat16
@@ -92,7 +93,7 @@ def main():
         print(json.dumps({"metric": "denoise_steps_per_sec", "workload": "HunyuanVideo-1.5 720p x 129f (118800 latent + 1985 condition "
                           "tokens, d=2048, 16 heads, %d dual-stream blocks), CFG on: 2 forwards + combine + Euler per step" % a.layers,
                           "value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "n_gpus": world,
-                          "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}", "steps": a.steps, "warmup": a.warmup, "dtype": "bf16",
+                          "parallelism": f"cfg{par.cfg_size} x sp{par.sp_size}", "exchange": "fused peer memory" if (a.p2p and par.sp_size > 1) else "nccl", "steps": a.steps, "warmup": a.warmup, "dtype": "bf16",
                           "data": "synthetic", "clocks": clocks, "algorithmic_flops_per_step": fl, "tflops": fl / ms / 1e9,
                           "tflops_per_gpu": fl / ms / 1e9 / world, "frac_of_peak_per_gpu": fl / ms / 1e9 / world / peak, "peak": peak,
                           "gpu_launches_per_step_rank0": ops.launch_count // a.steps, "finite": bool(torch.isfinite(y).all()),

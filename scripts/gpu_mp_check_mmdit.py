@@ -3,7 +3,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
         scripts/gpu_mp_check_mmdit.py
 
-On every rank: (1) sequence-parallel HunyuanVideo-1.5 forward == single-GPU forward, (2) the same for QwenImage (edit, two
+On every rank: (1) sequence-parallel HunyuanVideo-1.5 forward == single-GPU forward (NCCL exchange and the exchange fused into
+the kernels over NVLink peer memory), (2) the same for QwenImage (edit, two
 images), (3) CFG x SP hy15_denoise == the sequential loop, (4) tile-parallel HunyuanVideo-1.5 VAE decode == single-GPU
 tiled decode.  Prints one JSON line from rank 0."""
 import json
@@ -59,6 +60,11 @@ def main():
     single = m(x, t, image_embeds=img, return_dict=False, **kw)[0]
     sharded = m(x, t, image_embeds=img, return_dict=False, parallel=par_sp, **kw)[0]
     res["hy15_sp_max_abs_diff"] = (single.float() - sharded.float()).abs().max().item()
+    # the same with the exchange fused into the kernels over NVLink peer memory (parallel.JointPeerExchange), twice (buffer reuse)
+    par_p2p = ParallelContext.create(use_cfg=False, use_p2p=True)
+    for rep in range(2):
+        fused = m(x, t, image_embeds=img, return_dict=False, parallel=par_p2p, **kw)[0]
+        res[f"hy15_sp_p2p_run{rep}_max_abs_diff"] = (single.float() - fused.float()).abs().max().item()
 
     # 2. QwenImage edit: 64 + 32 image tokens, 13 text tokens
     qcfg = dict(dim=512, heads=4, num_layers=2, in_channels=16, out_channels=4, joint_dim=48)
@@ -69,7 +75,10 @@ def main():
     qx, qe = torch.randn(1, 96, 16, generator=g).to(dev, bf), torch.randn(1, 13, 48, generator=g).to(dev, bf)
     qt = torch.tensor([0.5], device=dev)
     qkw = dict(hidden_states=qx, encoder_hidden_states=qe, timestep=qt, img_shapes=[shapes], txt_seq_lens=[13], return_dict=False)
-    res["qwen_sp_max_abs_diff"] = (q(**qkw)[0].float() - q(parallel=par_sp, **qkw)[0].float()).abs().max().item()
+    q_single = q(**qkw)[0]
+    res["qwen_sp_max_abs_diff"] = (q_single.float() - q(parallel=par_sp, **qkw)[0].float()).abs().max().item()
+    for rep in range(2):   # text rows FIRST in QwenImage's joint sequence: the replicated rows lead
+        res[f"qwen_sp_p2p_run{rep}_max_abs_diff"] = (q_single.float() - q(parallel=par_p2p, **qkw)[0].float()).abs().max().item()
 
     # 3. CFG x SP denoise loop (HunyuanVideo-1.5: latents 4 ch + cond 4 ch + mask 1 ch = 9 input channels)
     lat = torch.randn(1, 4, 4, 8, 8, generator=g).to(dev, bf)

@@ -405,6 +405,37 @@ def test_scatter_kernels_addressing_on_one_gpu(ops):
 
 
 # ------------------------------------------------------------------------------------------------ composite C entry points
+@pytest.mark.parametrize("rep_first", [False, True])
+def test_joint_scatter_addressing_on_one_gpu(ops, rep_first):
+    """b200_attn_fwd_scatter_joint (the heads -> tokens exchange of the dual-stream families): two "peers" = two buffers on this
+    GPU.  Token-sharded image rows land in their owner's buffer, the replicated text rows in EVERY buffer, each buffer in its
+    local joint order (text first for Flux / QwenImage, last for HunyuanVideo-1.5); ragged text length."""
+    import ctypes
+
+    torch.manual_seed(11)
+    heads_total, hp, npeer, n_local, n_txt, d = 4, 2, 2, 160, 37, 512
+    S = npeer * n_local + n_txt
+    q, k, v = (torch.randn(1, hp, S, 128, device=DEV, dtype=torch.bfloat16) for _ in range(3))
+    ref = ops.attention(q, k, v)                                    # [1, hp, S, 128]
+    bufs = [torch.zeros(n_txt + n_local, d, device=DEV, dtype=torch.bfloat16) for _ in range(npeer)]
+    peers = (ctypes.c_void_p * npeer)(*[b.data_ptr() for b in bufs])
+    head_off = 1                                                   # this "rank" owns heads 1..2 of 4
+    ops.attention_scatter(q, k, v, peers, npeer, n_local, head_off, d, rep_rows=n_txt, rep_first=rep_first)
+    torch.cuda.synchronize()
+    rows = ref[0].transpose(0, 1).reshape(S, hp * 128)              # [S, hp*128]
+    img = rows[n_txt:] if rep_first else rows[:npeer * n_local]
+    txt = rows[:n_txt] if rep_first else rows[npeer * n_local:]
+    cols = slice(head_off * 128, (head_off + hp) * 128)
+    for r, b in enumerate(bufs):
+        got_txt = b[:n_txt, cols] if rep_first else b[n_local:, cols]
+        got_img = b[n_txt:, cols] if rep_first else b[:n_local, cols]
+        assert torch.equal(got_txt, txt)
+        assert torch.equal(got_img, img[r * n_local:(r + 1) * n_local])
+        other = torch.ones(d, dtype=torch.bool, device=DEV)
+        other[cols] = False
+        assert not b[:, other].any()                               # nothing outside this rank's head columns
+
+
 def test_composite_call_sites_equal_their_parts(ops):
     """b200_qkv_rmsnorm_rope / b200_mlp_gelu / b200_ln_modulate (SURVEY 8b granularity) enqueue exactly the kernels of
     the fine-grained entry points: results must be bit-identical."""
