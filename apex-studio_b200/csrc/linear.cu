@@ -75,6 +75,7 @@ struct Params {
   int bias_row;
   int tiles_m, tiles_n;
   int tma_store; // 1: bf16 output written through shared memory + TMA (128-byte lines) instead of 16-byte stores per lane
+  int c_vec32;   // rows of C are 32-byte aligned (bf16 outputs): the direct epilogues use 32-byte loads / stores
   int group_m;   // row-tiles per rasterisation group (the A rows of a group stay in L2 while its n-tiles are swept)
   int panel_n;   // column-tiles per panel: the W panel (panel_n x BN x K) stays in L2 while ALL row groups sweep it
 };
@@ -408,9 +409,22 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // residual stream update: h = h + gate * (acc + bias), fp32, one rounding.
             if (row_ok) {
               if (full_chunk) {
+                // The 64 bytes of h this thread updates are loaded up front -- as two 32-byte (full-sector) loads when the row
+                // is 32-byte aligned -- and written back the same way.  (One thread owns one output row: every warp-wide
+                // access touches 32 different lines, and interleaved 16-byte load / store pairs on the same pointer kept four
+                // dependent L2 round trips per chunk in flight one at a time.)
+                uint4 hv[4];
+                if (p.c_vec32) {
+                  ld_global_v8(cp, *reinterpret_cast<uint4(*)[2]>(&hv[0]));
+                  ld_global_v8(cp + 16, *reinterpret_cast<uint4(*)[2]>(&hv[2]));
+                } else {
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) hv[q4] = reinterpret_cast<const uint4*>(cp)[q4];
+                }
+                uint4 ov[4];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                  uint4 h = reinterpret_cast<const uint4*>(cp)[q4];
+                  const uint4 h = hv[q4];
                   float g[8];
                   if (p.gate != nullptr) {
                     uint4 gg = __ldg(reinterpret_cast<const uint4*>(p.gate + col0) + q4);
@@ -426,7 +440,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                   o.y = pack_bf16x2(bf16_lo(h.y) + g[2] * vv[2], bf16_hi(h.y) + g[3] * vv[3]);
                   o.z = pack_bf16x2(bf16_lo(h.z) + g[4] * vv[4], bf16_hi(h.z) + g[5] * vv[5]);
                   o.w = pack_bf16x2(bf16_lo(h.w) + g[6] * vv[6], bf16_hi(h.w) + g[7] * vv[7]);
-                  reinterpret_cast<uint4*>(cp)[q4] = o;
+                  ov[q4] = o;
+                }
+                if (p.c_vec32) {
+                  st_global_v8(cp, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
+                  st_global_v8(cp + 16, *reinterpret_cast<uint32_t(*)[8]>(&ov[2]));
+                } else {
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) reinterpret_cast<uint4*>(cp)[q4] = ov[q4];
                 }
               } else {
 #pragma unroll
@@ -439,15 +460,21 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
           } else if (row_ok) {
             if (full_chunk) {
+              uint4 ov[4];
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4) {
                 float* vv = v + q4 * 8;
-                uint4 o;
-                o.x = pack_bf16x2(vv[0], vv[1]);
-                o.y = pack_bf16x2(vv[2], vv[3]);
-                o.z = pack_bf16x2(vv[4], vv[5]);
-                o.w = pack_bf16x2(vv[6], vv[7]);
-                reinterpret_cast<uint4*>(cp)[q4] = o;
+                ov[q4].x = pack_bf16x2(vv[0], vv[1]);
+                ov[q4].y = pack_bf16x2(vv[2], vv[3]);
+                ov[q4].z = pack_bf16x2(vv[4], vv[5]);
+                ov[q4].w = pack_bf16x2(vv[6], vv[7]);
+              }
+              if (p.c_vec32) {
+                st_global_v8(cp, *reinterpret_cast<uint32_t(*)[8]>(&ov[0]));
+                st_global_v8(cp + 16, *reinterpret_cast<uint32_t(*)[8]>(&ov[2]));
+              } else {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) reinterpret_cast<uint4*>(cp)[q4] = ov[q4];
               }
             } else {
 #pragma unroll
@@ -569,6 +596,7 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   }
   Params p;
   p.tma_store = use_tma_store ? 1 : 0;
+  p.c_vec32 = (epilogue != B200_EPI_BIAS_F32 && (ldc % 16) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0) ? 1 : 0;
   p.M = M; p.N = N; p.K = K;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
   p.gate = reinterpret_cast<const __nv_bfloat16*>(gate);
