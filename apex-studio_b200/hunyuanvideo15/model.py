@@ -89,6 +89,7 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
         self.w: Dict[str, torch.Tensor] = {}
         self._mod_rows: Dict[str, Tuple[int, int]] = {}
         self._rope_cache: Dict[Tuple, torch.Tensor] = {}
+        self._cond_plans: Dict[Tuple, dict] = {}      # per-prompt timestep-independent condition work (_condition_plan)
         self._ws: Optional[JointWorkspace] = None
         self._k_pad = 0
         self.dtype = torch.bfloat16
@@ -137,7 +138,12 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
             keys += [m + ".weight", m + ".bias"]
         return keys
 
+    def invalidate_caches(self) -> None:
+        """Weights changed (load, LoRA merge): drop what was computed from them."""
+        self._cond_plans.clear()
+
     def _finish_weights(self, w: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        self.invalidate_caches()
         c = self.config
         # Conv3d(kernel = stride = patch) as a GEMM over [tokens, C*pt*p*p]; K padded to a multiple of 8 for TMA (65 -> 72)
         pw = w["x_embedder.proj.weight"].reshape(c.inner_dim, -1)
@@ -295,30 +301,48 @@ class HunyuanVideo15Transformer3DModel(LoraHostMixin):
             self._lin(f1, q + ".ff.net.2", ops.EPI_GATE_RES, out=h, gate=gate_mlp)
         return h
 
-    def condition_tokens(self, text, mask, text2, mask2, image_embeds, timestep) -> torch.Tensor:
-        """model.py:1011-1101 for ONE sample: text [L1, text_dim], mask [L1], text2 [L2, text2_dim], mask2 [L2],
-        image_embeds [L3, image_dim] -> [L3 + L2 + L1, dim] in the reference's valid-first order."""
+    def _condition_plan(self, text, mask, text2, mask2, image_embeds) -> dict:
+        """Everything of condition_tokens that does not depend on the timestep, computed ONCE per prompt: the valid counts and
+        the t2v flag (host syncs), the compacted text tokens, and the image / byT5 branches.  Keyed on the identity and version
+        of the five input tensors (the denoise loop passes the same device tensors every step); the entry keeps references to
+        them, so a key cannot be recycled by another tensor while it is cached.  Without it every forward stalled the launch
+        queue on four device -> host reads per sample and could not be captured in a CUDA graph."""
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype, str(t.device)) for t in (text, mask, text2, mask2, image_embeds))
+        plan = self._cond_plans.get(key)
+        if plan is not None:
+            return plan
         w, d = self.w, self.config.inner_dim
         emb = w["cond_type_embed.weight"]
         v1, v2 = mask.bool().to(self.device), mask2.bool().to(self.device)
-        n_pad = int((~v1).sum()) + int((~v2).sum())
-        parts_valid, parts_invalid = [], []
-        is_t2v = bool(torch.all(image_embeds == 0))
-        if is_t2v:     # image stream: projection * 0 + type embedding, every token "invalid" (kept, not zeroed, :1036-1043)
-            parts_invalid.append(emb[2][None, :].expand(image_embeds.shape[0], d))
+        n1, n2 = int(v1.sum()), int(v2.sum())
+        plan = {"keep": (text, mask, text2, mask2, image_embeds), "n_pad": (v1.numel() - n1) + (v2.numel() - n2),
+                "valid": [], "invalid": [], "text_valid": text[v1].contiguous() if n1 > 0 else None}
+        if bool(torch.all(image_embeds == 0)):   # t2v: projection * 0 + type embedding, every token "invalid" (kept, not zeroed, :1036-1043)
+            plan["invalid"].append(emb[2][None, :].expand(image_embeds.shape[0], d))
         else:
             h3 = self._ln(image_embeds, "image_embedder.norm_in", 1e-5)
             h3 = self._lin(self._lin(h3, "image_embedder.linear_1", ops.EPI_GELU_ERF), "image_embedder.linear_2")
-            parts_valid.append(self._ln(h3, "image_embedder.norm_out", 1e-5) + emb[2])
-        if int(v2.sum()) > 0:
+            plan["valid"].append(self._ln(h3, "image_embedder.norm_out", 1e-5) + emb[2])
+        if n2 > 0:
             h2 = self._ln(text2[v2].contiguous(), "context_embedder_2.norm", 1e-5)
             h2 = self._lin(self._lin(h2, "context_embedder_2.linear_1", ops.EPI_GELU_ERF), "context_embedder_2.linear_2",
                            ops.EPI_GELU_ERF)
-            parts_valid.append(self._lin(h2, "context_embedder_2.linear_3") + emb[1])
-        if int(v1.sum()) > 0:
-            parts_valid.append(self.token_refiner(text[v1].contiguous(), timestep) + emb[0])
-        zeros = torch.zeros(n_pad, d, dtype=torch.bfloat16, device=self.device)
-        return torch.cat(parts_valid + parts_invalid + [zeros], dim=0)
+            plan["valid"].append(self._lin(h2, "context_embedder_2.linear_3") + emb[1])
+        plan["zeros"] = torch.zeros(plan["n_pad"], d, dtype=torch.bfloat16, device=self.device)
+        if len(self._cond_plans) >= 8:           # cond / uncond of a few prompts; oldest first out
+            self._cond_plans.pop(next(iter(self._cond_plans)))
+        self._cond_plans[key] = plan
+        return plan
+
+    def condition_tokens(self, text, mask, text2, mask2, image_embeds, timestep) -> torch.Tensor:
+        """model.py:1011-1101 for ONE sample: text [L1, text_dim], mask [L1], text2 [L2, text2_dim], mask2 [L2],
+        image_embeds [L3, image_dim] -> [L3 + L2 + L1, dim] in the reference's valid-first order.  Only the token refiner
+        (it is modulated by the timestep) runs per step; the rest comes from the per-prompt plan."""
+        plan = self._condition_plan(text, mask, text2, mask2, image_embeds)
+        parts = list(plan["valid"])
+        if plan["text_valid"] is not None:
+            parts.append(self.token_refiner(plan["text_valid"], timestep) + self.w["cond_type_embed.weight"][0])
+        return torch.cat(parts + plan["invalid"] + [plan["zeros"]], dim=0)
 
     # ------------------------------------------------------------------------------------ forward
     def _rope(self, grid: Tuple[int, int, int]) -> torch.Tensor:

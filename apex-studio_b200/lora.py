@@ -285,6 +285,7 @@ class LoraHostMixin:
         return self._lora_base[module]
 
     def _remerge(self, modules: Optional[Iterable[str]] = None) -> None:
+        getattr(self, "invalidate_caches", lambda: None)()   # models may cache results computed from the weights
         adapters = self._lora_state()
         if modules is None:
             modules = sorted(set(self._lora_base) | {m for ad in adapters.values() for m in ad.modules})

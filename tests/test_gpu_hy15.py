@@ -90,3 +90,28 @@ def test_hy15_full_width_one_block_vs_exact_oracle():
     ours, theirs = rel_l2(out, exact), rel_l2(bf, exact)
     assert torch.isfinite(out).all() and tuple(out.shape) == (1, 32, 5, 16, 20)
     assert ours <= max(1e-3, 1.5 * theirs), (ours, theirs)
+
+
+def test_hy15_condition_plan_is_cached_per_prompt_and_invalidated():
+    """The timestep-independent part of condition_tokens (valid counts, t2v flag, compacted tokens, image / byT5 branches) is
+    computed once per prompt: the same device tensors hit the cached plan (no host syncs, same result), an in-place change
+    of a mask or new weights miss it."""
+    name = "hy15_t2v"
+    cfg, g = CONFIGS[name], load(name)
+    w32 = hy15_dit.make_weights(**cfg, seed=1234, dtype=torch.float32)
+    m = _model(cfg, w32)
+    x, t, text, mask, text2, mask2, img = inputs(g, torch.bfloat16)
+    dev_args = [text[0].to(DEV), mask[0].to(DEV), text2[0].to(DEV), mask2[0].to(DEV), img[0].to(DEV)]
+    a = m.condition_tokens(*dev_args, t.to(DEV))
+    assert len(m._cond_plans) == 1
+    b = m.condition_tokens(*dev_args, t.to(DEV))
+    assert len(m._cond_plans) == 1 and torch.equal(a, b)
+    c = m.condition_tokens(*dev_args, (t * 0.5).to(DEV))            # only the token refiner depends on the timestep
+    assert len(m._cond_plans) == 1 and not torch.equal(a, c)
+    n_valid = int(dev_args[1].sum())
+    dev_args[1][n_valid - 1] = 0                                    # in-place edit of the mask: a new plan, one token fewer
+    d = m.condition_tokens(*dev_args, t.to(DEV))
+    assert len(m._cond_plans) == 2 and d.shape == a.shape
+    assert d[-1].abs().max().item() == 0 and not torch.equal(a, d)
+    m.load_state_dict(w32, device=DEV)
+    assert len(m._cond_plans) == 0
