@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_swiglu": (_i, [_p, _p, _i, _i, _i64, _i64, _p]),
     "b200_pad_norm_silu_cl": (_i, [_p, _p, _p] + [_i] * 8 + [_p]),
     "b200_conv3d_cl_padded": (_i, [_p, _p, _p, _p, _p] + [_i] * 10 + [_p]),
+    "b200_conv3d_cl_norm_silu": (_i, [_p, _p, _p, _p, _p] + [_i] * 8 + [_p]),
     "b200_dcae_upsample_cl": (_i, [_p, _p, _p] + [_i] * 6 + [_p]),
     "b200_softmax_rows_block_causal": (_i, [_p, _p, _i, _i, _i64, _i64, _f, _i, _p]),
     "b200_blend_tile_noclamp": (_i, [_p, _p, _p, _p] + [_i] * 14 + [_p]),

@@ -56,6 +56,10 @@ struct Params {
   int pad_t, pad_h, pad_w;
   int TB, tblocks;            // conv3d_tb_kernel: output frames per CTA block, ceil(T / TB)
   int vec32;                  // channels-last rows of out / residual are 32-byte aligned: 32-byte loads and stores
+  // Fused consumer (WanResidualBlock: conv1 -> norm2 -> SiLU, vae/wan/model.py:404-413): non-null = the epilogue applies
+  // WanRMS_norm (x / max(||x||_2, 1e-12) * sqrt(C) * gamma over the channels of a pixel) + SiLU to the bf16-rounded conv
+  // output and stores only that.  Needs the whole channel vector in one N tile (tiles_n == 1).
+  const __nv_bfloat16* norm_gamma;
 };
 
 template <int BK>
@@ -153,6 +157,72 @@ __device__ __forceinline__ void store_rows(const Params& p, int t, int h0, int w
       for (int j = 0; j < 16; ++j)
         if (n0 + j < p.Cvalid)
           op[(static_cast<int64_t>(n0 + j) * p.T + t) * frame_px + pix] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+// Epilogue with the fused RMS-norm + SiLU (Params::norm_gamma): two passes over the accumulator row -- sum of squares of the
+// bf16-rounded conv output (what the unfused path stores and the norm kernel reads back), then normalise, SiLU, store.  Saves
+// the norm kernel's launch and its read + write pass over the activation (HBM-bound: 2 GB per launch at the 96-channel stage).
+__device__ __forceinline__ void store_rows_norm(const Params& p, int t, int h0, int w0, uint32_t t_addr, int quad, int lane) {
+  const int64_t frame_px = static_cast<int64_t>(p.H) * p.W;
+  const int r = quad * 32 + lane;
+  const int h = h0 + r / p.BW;
+  const int w = w0 + r % p.BW;
+  const bool ok = (h < p.H) && (w < p.W);
+  const int64_t pix = static_cast<int64_t>(h) * p.W + w;
+  auto load_chunk = [&](int c0, float (&v)[16]) {
+    uint32_t rr[16];
+    tmem_ld_x16(t_addr + c0, rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+    if (p.bias != nullptr) {
+      const uint4* bp = reinterpret_cast<const uint4*>(p.bias + c0);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4 b = __ldg(bp + q);
+        v[q * 8 + 0] += bf16_lo(b.x); v[q * 8 + 1] += bf16_hi(b.x);
+        v[q * 8 + 2] += bf16_lo(b.y); v[q * 8 + 3] += bf16_hi(b.y);
+        v[q * 8 + 4] += bf16_lo(b.z); v[q * 8 + 5] += bf16_hi(b.z);
+        v[q * 8 + 6] += bf16_lo(b.w); v[q * 8 + 7] += bf16_hi(b.w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));   // the conv output as the reference stores it
+  };
+  float ss = 0.f;
+  for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    float v[16];
+    load_chunk(c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ss += v[j] * v[j];
+  }
+  const float inv = sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+  for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    float v[16];
+    load_chunk(c0, v);
+    if (!ok) continue;
+    const uint4* gp = reinterpret_cast<const uint4*>(p.norm_gamma + c0);
+    uint32_t ov[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint4 g = __ldg(gp + q);
+      const float gg[8] = {bf16_lo(g.x), bf16_hi(g.x), bf16_lo(g.y), bf16_hi(g.y), bf16_lo(g.z), bf16_hi(g.z), bf16_lo(g.w), bf16_hi(g.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = v[q * 8 + j] * inv * gg[j];
+        v[q * 8 + j] = 0.5f * y * (1.0f + fast_tanh(0.5f * y));   // SiLU as in vae_ops.cu (one MUFU op per element)
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ov[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(t) * frame_px + pix) * p.Cout + c0;
+    if (p.vec32) {
+      st_global_v8(op, ov);
+    } else {
+      reinterpret_cast<uint4*>(op)[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      reinterpret_cast<uint4*>(op)[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
     }
   }
 }
@@ -288,7 +358,8 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      store_rows(p, t, h0, w0, tn, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN_MAX, quad, lane);
+      if (p.norm_gamma != nullptr) store_rows_norm(p, t, h0, w0, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN_MAX, quad, lane);
+      else store_rows(p, t, h0, w0, tn, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN_MAX, quad, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -677,7 +748,7 @@ int launch(const void* x, const void* wt, Params& p, cudaStream_t st) {
 
 static int conv3d_cl_impl(const void* x, const void* w, const void* bias, const void* residual, void* out, int T,
                           int H, int W, int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul,
-                          int out_t_off, int c_split, int c_valid, int prepadded, void* stream) {
+                          int out_t_off, int c_split, int c_valid, int prepadded, void* stream, const void* norm_gamma = nullptr) {
   using namespace b200;
   using namespace b200::conv;
   if (!x || !w || !out) return B200_ERR_ARG;
@@ -706,6 +777,12 @@ static int conv3d_cl_impl(const void* x, const void* w, const void* bias, const 
   p.tiles_h = (H + p.BH - 1) / p.BH;
   p.tiles_n = Cout / bn;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.norm_gamma = reinterpret_cast<const __nv_bfloat16*>(norm_gamma);
+  if (norm_gamma != nullptr) {
+    // the fused norm needs a pixel's whole channel vector in one accumulator row and the plain channels-last store
+    if (p.tiles_n != 1 || residual != nullptr || out_mode != 0 || c_split != Cout || out_t_mul != 1 || out_t_off != 0) return B200_ERR_SHAPE;
+    if (reinterpret_cast<uintptr_t>(norm_gamma) & 15) return B200_ERR_ALIGN;
+  }
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = out;
   p.out_mode = out_mode;
@@ -739,7 +816,7 @@ static int conv3d_cl_impl(const void* x, const void* w, const void* bias, const 
   const int tb_cap = tb_mode < 0 ? 0 : (tb_mode > TB_MAX ? TB_MAX : tb_mode);
   if (tb > tb_cap) tb = tb_cap;
   if (tb > T) tb = T;
-  p.TB = (KT >= 2 && KT <= TB_KT_MAX && bn <= bn_limit_tb && tb >= 2) ? tb : 1;
+  p.TB = (KT >= 2 && KT <= TB_KT_MAX && bn <= bn_limit_tb && tb >= 2 && norm_gamma == nullptr) ? tb : 1;
   p.tblocks = (T + p.TB - 1) / p.TB;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (bk == 64) return launch<64, 1>(x, w, p, st);
@@ -752,6 +829,12 @@ extern "C" int b200_conv3d_cl(const void* x, const void* w, const void* bias, co
                               int out_t_off, int c_split, int c_valid, void* stream) {
   return conv3d_cl_impl(x, w, bias, residual, out, T, H, W, Cin, Cout, KT, KH, KW, out_mode, out_t_mul, out_t_off, c_split,
                         c_valid, 0, stream);
+}
+
+extern "C" int b200_conv3d_cl_norm_silu(const void* x, const void* w, const void* bias, const void* gamma, void* out, int T,
+                                        int H, int W, int Cin, int Cout, int KT, int KH, int KW, void* stream) {
+  if (!gamma) return B200_ERR_ARG;
+  return conv3d_cl_impl(x, w, bias, nullptr, out, T, H, W, Cin, Cout, KT, KH, KW, 0, 1, 0, Cout, Cout, 0, stream, gamma);
 }
 
 extern "C" int b200_conv3d_cl_padded(const void* x_padded, const void* w, const void* bias, const void* residual, void* out,

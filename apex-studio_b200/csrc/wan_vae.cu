@@ -50,6 +50,18 @@ struct Ctx {
 
 inline int64_t bf16_bytes(int64_t n) { return n * 2; }
 
+// conv1 -> norm2 -> SiLU of a residual block as ONE kernel (b200_conv3d_cl_norm_silu) when the conv keeps a pixel's channel
+// vector in one N tile: Cout <= 256 (96, 192; the 384-channel stage runs two N tiles of 192).  B200_VAE_FUSE_NORM=0: never
+// (the A/B partner; vae/wan.py applies the same rule so that both host paths stay bit-identical).
+inline bool conv_norm_fusable(int cout) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* ev = getenv("B200_VAE_FUSE_NORM");
+    mode = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  return mode == 1 && cout <= 256 && (cout % 16) == 0;
+}
+
 // y = conv2(silu(norm2(conv1(silu(norm1(x)))))) + shortcut(x)      (WanResidualBlock)
 void* res_block(Ctx& c, const void* x, const B200WanResBlock& w, int T, int H, int W) {
   const int64_t px = static_cast<int64_t>(T) * H * W;
@@ -68,8 +80,12 @@ void* res_block(Ctx& c, const void* x, const B200WanResBlock& w, int T, int H, i
   void* y = a.take(bf16_bytes(px * w.cout));
   if (!out || !n || !y) { c.rc = B200_ERR_ARG; return nullptr; }
   VAE_TRY(b200_rmsnorm_silu_cl(x, n, w.norm1_gamma, px, w.cin, 1, c.stream));
-  VAE_TRY(b200_conv3d_cl(n, w.conv1_w, w.conv1_b, nullptr, y, T, H, W, w.cin, w.cout, 3, 3, 3, 0, 1, 0, w.cout, w.cout, c.stream));
-  VAE_TRY(b200_rmsnorm_silu_cl(y, y, w.norm2_gamma, px, w.cout, 1, c.stream));
+  if (conv_norm_fusable(w.cout)) {   // conv1 -> norm2 -> SiLU in one kernel (the conv output has no other consumer)
+    VAE_TRY(b200_conv3d_cl_norm_silu(n, w.conv1_w, w.conv1_b, w.norm2_gamma, y, T, H, W, w.cin, w.cout, 3, 3, 3, c.stream));
+  } else {
+    VAE_TRY(b200_conv3d_cl(n, w.conv1_w, w.conv1_b, nullptr, y, T, H, W, w.cin, w.cout, 3, 3, 3, 0, 1, 0, w.cout, w.cout, c.stream));
+    VAE_TRY(b200_rmsnorm_silu_cl(y, y, w.norm2_gamma, px, w.cout, 1, c.stream));
+  }
   VAE_TRY(b200_conv3d_cl(y, w.conv2_w, w.conv2_b, h, out, T, H, W, w.cout, w.cout, 3, 3, 3, 0, 1, 0, w.cout, w.cout, c.stream));
   c.end_block();
   return out;

@@ -20,6 +20,8 @@ Design (DESIGN.md section "VAE"):
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -56,15 +58,33 @@ def _stream() -> int:
 # ---------------------------------------------------------------------------------------------------------
 # thin wrappers over the C ABI
 # ---------------------------------------------------------------------------------------------------------
+def conv_norm_fusable(cout: int) -> bool:
+    """conv1 -> norm2 -> SiLU of a residual block as one kernel (b200_conv3d_cl_norm_silu): the conv must keep a pixel's
+    channel vector in one N tile (cout <= 256); B200_VAE_FUSE_NORM=0 disables it (the rule of csrc/wan_vae.cu)."""
+    return os.environ.get("B200_VAE_FUSE_NORM", "1") != "0" and cout <= 256 and cout % 16 == 0
+
+
 def conv3d_cl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], taps: Tuple[int, int, int], cout: int, *,
               residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, planar_channels: int = 0,
-              interleave: bool = False) -> torch.Tensor:
+              interleave: bool = False, norm_gamma: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [T,H,W,Cin] channels-last bf16, w [taps*cout, Cin] tap-major.  Returns [T,H,W,cout] (or, with
-    ``interleave``, writes frames 1.. of ``out`` [1+2T,H,W,cout/2]; or planar [planar_channels,T,H,W])."""
+    ``interleave``, writes frames 1.. of ``out`` [1+2T,H,W,cout/2]; or planar [planar_channels,T,H,W]).
+    ``norm_gamma``: WanRMS_norm + SiLU of the conv output fused into the epilogue (only that is returned)."""
     T, H, W, cin = x.shape
     kt, kh, kw = taps
     if not x.is_contiguous():
         raise ValueError("conv3d_cl needs a contiguous channels-last input")
+    if norm_gamma is not None:
+        if residual is not None or planar_channels or interleave:
+            raise ValueError("norm_gamma fuses the norm of a plain conv output (no residual / planar / interleave)")
+        if out is None:
+            out = torch.empty(T, H, W, cout, dtype=torch.bfloat16, device=x.device)
+        lib = _lib.load()
+        rc = lib.b200_conv3d_cl_norm_silu(x.data_ptr(), w.data_ptr(), None if bias is None else bias.data_ptr(),
+                                          norm_gamma.data_ptr(), out.data_ptr(), T, H, W, cin, cout, kt, kh, kw, _stream())
+        _lib.check(rc, "b200_conv3d_cl_norm_silu")
+        ops._count()
+        return out
     if planar_channels:
         if out is None:
             out = torch.empty(planar_channels, T, H, W, dtype=torch.bfloat16, device=x.device)
@@ -310,9 +330,12 @@ class AutoencoderKLWan:
         else:
             h = x
         n = rmsnorm_silu_cl(x, w[p + ".norm1.gamma"])
-        y = conv3d_cl(n, w[p + ".conv1.weight"], w[p + ".conv1.bias"], (3, 3, 3), cout)
-        del n
-        n = rmsnorm_silu_cl(y, w[p + ".norm2.gamma"], out=y)
+        if conv_norm_fusable(cout):     # conv1 -> norm2 -> SiLU in one kernel (same rule as csrc/wan_vae.cu)
+            n = conv3d_cl(n, w[p + ".conv1.weight"], w[p + ".conv1.bias"], (3, 3, 3), cout, norm_gamma=w[p + ".norm2.gamma"])
+        else:
+            y = conv3d_cl(n, w[p + ".conv1.weight"], w[p + ".conv1.bias"], (3, 3, 3), cout)
+            del n
+            n = rmsnorm_silu_cl(y, w[p + ".norm2.gamma"], out=y)
         return conv3d_cl(n, w[p + ".conv2.weight"], w[p + ".conv2.bias"], (3, 3, 3), cout, residual=h)
 
     def _attn_block(self, x: torch.Tensor, p: str) -> torch.Tensor:

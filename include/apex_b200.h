@@ -193,6 +193,16 @@ int b200_conv3d_cl(const void* x, const void* w, const void* bias, const void* r
                    int Cin, int Cout, int KT, int KH, int KW, int out_mode, int out_t_mul, int out_t_off, int c_split,
                    int c_valid, void* stream);
 
+/*
+ * b200_conv3d_cl followed by WanRMS_norm + SiLU of its output in the SAME kernel: conv1 -> norm2 -> nonlinearity of
+ * WanResidualBlock (vae/wan/model.py:404-413; the conv output has no other consumer).  The epilogue rounds the conv result to
+ * bf16 as the reference stores it, normalises over the channels of the pixel, applies gamma and SiLU, and stores only that.
+ * Needs Cout in one N tile (Cout % 16 == 0, Cout <= 256 and a divisor rule that keeps it whole: 96, 192; 384 -> B200_ERR_SHAPE,
+ * the caller then issues conv + b200_rmsnorm_silu_cl).
+ */
+int b200_conv3d_cl_norm_silu(const void* x, const void* w, const void* bias, const void* gamma, void* out, int T, int H,
+                             int W, int Cin, int Cout, int KT, int KH, int KW, void* stream);
+
 /* y = x / max(||x||_2 over channels, 1e-12) * sqrt(C) * gamma, then SiLU if `silu` (WanRMS_norm :216-222 + the
  * nonlinearity at :404-405, :1005-1006); x, y: [pixels, C]; gamma: [C]. */
 int b200_rmsnorm_silu_cl(const void* x, void* y, const void* gamma, int64_t pixels, int C, int silu, void* stream);

@@ -247,3 +247,38 @@ def test_preview_renderer_on_a_side_stream_equals_synchronous_decode():
     for frames, step in zip(got, pr.rendered_steps):
         ref = fn(lats[step]).cpu().numpy()
         assert frames.dtype == np.uint8 and frames.shape == ref.shape and (frames == ref).all()
+
+
+@pytest.mark.parametrize("T,H,W,cin,cout", [(5, 18, 16, 96, 96), (3, 20, 24, 192, 192), (4, 9, 21, 384, 192), (2, 16, 16, 96, 32)])
+def test_conv3d_fused_rmsnorm_silu_epilogue(T, H, W, cin, cout):
+    """b200_conv3d_cl_norm_silu (conv1 -> norm2 -> SiLU of WanResidualBlock in one kernel) vs the two-kernel path: the epilogue
+    normalises the bf16-rounded conv output exactly as the norm kernel reads it back; only the summation order of the squares
+    differs, so results agree to a bf16 ulp on all but a few elements.  Also against fp32 math of the whole chain."""
+    from apex_studio_b200.vae.wan import conv3d_cl, rmsnorm_silu_cl
+
+    g = torch.Generator().manual_seed(T * 10 + cout)
+    x = torch.randn(1, cin, T, H, W, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, 3, generator=g) * (27 * cin) ** -0.5).bfloat16()
+    b = (torch.randn(cout, generator=g) * 0.1).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(cout, generator=g)).bfloat16().to(DEV)
+    two = rmsnorm_silu_cl(conv3d_cl(_cl(x), _tap_major(w.float()), b.to(DEV), (3, 3, 3), cout), gamma)
+    one = conv3d_cl(_cl(x), _tap_major(w.float()), b.to(DEV), (3, 3, 3), cout, norm_gamma=gamma)
+    diff = (one.float() - two.float()).abs()
+    ulp = two.float().abs().clamp_min(1e-3) * 2.0 ** -7
+    assert (diff > ulp).float().mean().item() <= 2e-3 and rel_l2(one, two) <= 2e-3
+    conv = wan_vae.causal_conv3d(x.float(), {"c.weight": w.float(), "c.bias": b.float()}, "c")[0]     # [C,T,H,W] fp32
+    ref = torch.nn.functional.normalize(conv, dim=0) * cout ** 0.5 * gamma.float().cpu().view(-1, 1, 1, 1)
+    ref = torch.nn.functional.silu(ref).permute(1, 2, 3, 0)
+    assert rel_l2(one, ref) <= 6e-3
+
+
+def test_conv3d_fused_norm_rejects_split_channel_tiles():
+    """384 output channels run as two N tiles of 192: the pixel's channel vector is not in one accumulator row."""
+    from apex_studio_b200 import _lib
+    from apex_studio_b200.vae.wan import conv3d_cl, conv_norm_fusable
+
+    assert conv_norm_fusable(96) and conv_norm_fusable(192) and not conv_norm_fusable(384)
+    x = torch.randn(2, 8, 8, 64, device=DEV).bfloat16()
+    w = torch.randn(27 * 384, 64, device=DEV).bfloat16()
+    with pytest.raises((ValueError, RuntimeError)):
+        conv3d_cl(x, w, None, (3, 3, 3), 384, norm_gamma=torch.ones(384, device=DEV).bfloat16())
