@@ -132,8 +132,6 @@ def test_attention_full_size_properties(ops):
 @pytest.mark.parametrize("M,N,K", [(1, 64, 64), (128, 256, 64), (300, 520, 264), (1000, 5120, 512), (75600, 64, 5120)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_linear_epilogues(ops, M, N, K, epi):
-    if M == 75600 and epi not in (0,):
-        pytest.skip("full-height case once")
     torch.manual_seed(M + N + K + epi)
     x = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
@@ -453,7 +451,9 @@ def test_composite_call_sites_equal_their_parts(ops):
     out = torch.empty(rows, 3 * dim, dtype=bf, device=DEV)
     n0 = ops.launch_count
     ops.qkv_rmsnorm_rope(x, wqkv, bqkv, wq, wk, rope, heads, 1e-6, out)
-    assert ops.launch_count - n0 == 3
+    # q and k share one batched norm launch when their weight vectors happen to be adjacent in memory ([2, dim] storage)
+    stacked = wk.data_ptr() == wq.data_ptr() + 2 * dim
+    assert ops.launch_count - n0 == (2 if stacked else 3)
     assert torch.equal(out, ref)
 
     w1, b1 = (torch.randn(ffn, dim, generator=g) * 0.05).to(DEV, bf), (torch.randn(ffn, generator=g) * 0.05).to(DEV, bf)
