@@ -98,31 +98,36 @@ void attn_block(Ctx& c, void* x, const B200WanAttn& w, int T, int H, int W) {
   const int64_t px = static_cast<int64_t>(T) * N;
   c.begin_block();
   Arena& a = c.out();
+  // The three weight GEMMs do not mix frames: q | k, V^T and the output projection run ONCE over all T frames (M = T * N rows)
+  // instead of once per frame; only the scores and P V are per frame.  66 launches instead of 126, and the projections fill the
+  // GPU (per frame they were 16-CTA grids).  Element-wise identical to the per-frame form (same K loop per output element).
   void* xn = a.take(bf16_bytes(px * C));
-  void* qk = a.take(bf16_bytes(static_cast<int64_t>(N) * 2 * C));
-  void* vT = a.take(bf16_bytes(static_cast<int64_t>(C) * N));
+  void* qk = a.take(bf16_bytes(px * 2 * C));                       // [T*N, 2C]
+  void* vT = a.take(bf16_bytes(static_cast<int64_t>(C) * px));     // [C, T*N]  (V^T of every frame side by side)
   void* s = a.take(static_cast<int64_t>(N) * N * 4);
   void* pm = a.take(bf16_bytes(static_cast<int64_t>(N) * N));
-  void* o = a.take(bf16_bytes(static_cast<int64_t>(N) * C));
+  void* o = a.take(bf16_bytes(px * C));                            // [T*N, C]
   if (!xn || !qk || !vT || !s || !pm || !o) { c.rc = B200_ERR_ARG; return; }
   VAE_TRY(b200_rmsnorm_silu_cl(x, xn, w.norm_gamma, px, C, 0, c.stream));
   const char* wq = static_cast<const char*>(w.to_qkv_w);
   const char* bq = static_cast<const char*>(w.to_qkv_b);
   const float scale = static_cast<float>(pow(static_cast<double>(C), -0.5));   // C ** -0.5 in double, rounded once (as the host path does)
+  const int M = static_cast<int>(px);
+  // q | k = xn Wqk^T + b  [T*N, 2C];  V^T = Wv xn^T + b (per-row bias)  [C, T*N]
+  VAE_TRY(b200_linear(xn, wq, bq, qk, nullptr, M, 2 * C, C, C, C, 2 * C, B200_EPI_BIAS, c.stream));
+  VAE_TRY(b200_linear(wq + bf16_bytes(static_cast<int64_t>(2) * C * C), xn, bq + bf16_bytes(2 * C), vT, nullptr, C, M, C, C, C, M,
+                      B200_EPI_BIAS | B200_EPI_ROW_BIAS, c.stream));
   for (int t = 0; t < T; ++t) {
-    const char* xt = static_cast<const char*>(xn) + bf16_bytes(static_cast<int64_t>(t) * N * C);
-    char* xo = static_cast<char*>(x) + bf16_bytes(static_cast<int64_t>(t) * N * C);
-    // q | k = xt Wqk^T + b  [N, 2C];  V^T = Wv xt^T + b (per-row bias)  [C, N]
-    VAE_TRY(b200_linear(xt, wq, bq, qk, nullptr, N, 2 * C, C, C, C, 2 * C, B200_EPI_BIAS, c.stream));
-    VAE_TRY(b200_linear(wq + bf16_bytes(static_cast<int64_t>(2) * C * C), xt, bq + bf16_bytes(2 * C), vT, nullptr, C, N, C, C, C, N,
-                        B200_EPI_BIAS | B200_EPI_ROW_BIAS, c.stream));
-    // scores = q k^T (fp32), P = softmax(scores / sqrt(C)), o = P V, x[t] += proj(o)
-    VAE_TRY(b200_linear(qk, static_cast<const char*>(qk) + bf16_bytes(C), nullptr, s, nullptr, N, N, C, 2 * C, 2 * C, N,
-                        B200_EPI_BIAS_F32, c.stream));
+    const char* qt = static_cast<const char*>(qk) + bf16_bytes(static_cast<int64_t>(t) * N * 2 * C);
+    const char* vt = static_cast<const char*>(vT) + bf16_bytes(static_cast<int64_t>(t) * N);
+    char* ot = static_cast<char*>(o) + bf16_bytes(static_cast<int64_t>(t) * N * C);
+    // scores = q k^T (fp32), P = softmax(scores / sqrt(C)), o = P V
+    VAE_TRY(b200_linear(qt, qt + bf16_bytes(C), nullptr, s, nullptr, N, N, C, 2 * C, 2 * C, N, B200_EPI_BIAS_F32, c.stream));
     VAE_TRY(b200_softmax_rows(static_cast<const float*>(s), pm, N, N, N, N, scale, c.stream));
-    VAE_TRY(b200_linear(pm, vT, nullptr, o, nullptr, N, C, N, N, N, C, B200_EPI_BIAS, c.stream));
-    VAE_TRY(b200_linear(o, w.proj_w, w.proj_b, xo, nullptr, N, C, C, C, C, C, B200_EPI_GATE_RES, c.stream));
+    VAE_TRY(b200_linear(pm, vt, nullptr, ot, nullptr, N, C, N, N, M, C, B200_EPI_BIAS, c.stream));
   }
+  // x += proj(o) for all frames
+  VAE_TRY(b200_linear(o, w.proj_w, w.proj_b, x, nullptr, M, C, C, C, C, C, B200_EPI_GATE_RES, c.stream));
   // x stays where it is: the block was in place, the other region only held temporaries
 }
 
