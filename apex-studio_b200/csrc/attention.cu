@@ -390,13 +390,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
    } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
-    if (leader && elect_one()) {
+    // ATTN_UNIFORM_ISSUE=1 (experiment, off): ALL 32 lanes of the MMA warp run the issue loop (waits, ring cursor, descriptor
+    // arithmetic) and one elected lane issues the tcgen05 instructions.  Warp-uniform control flow lets ptxas keep more of the
+    // descriptor arithmetic on the uniform datapath (R2UR 93 -> 51 per key tile) but the loop grows (329 -> 357 instructions)
+    // and 32 lanes poll every barrier: measured SLOWER, 1303 vs 1375 TFLOP/s on 40 x 75,600^2 and 1010 vs 1080 on the Wan
+    // cross-attention (profiles/r02_attn_uniform_issue_ab.log).  Default: only the elected lane runs the loop.
+#ifndef ATTN_UNIFORM_ISSUE
+#define ATTN_UNIFORM_ISSUE 0
+#endif
+    const bool issuer = elect_one();
+    if (leader && (ATTN_UNIFORM_ISSUE || issuer)) {
       const uint32_t tmem_base = read_tmem_base();
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(BQ * NCTA, BKV, 0);  // B = K tile, K-major
       constexpr uint32_t idesc_o = make_idesc_bf16_f32(BQ * NCTA, D, 1);    // B = V tile, MN-major
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t kv_addr = smem_u32(kv_smem);
       auto commit = [&](uint64_t* bar) {
+        if (!issuer) return;
         if constexpr (NCTA == 2) umma_commit_2sm(bar); else umma_commit(bar);
       };
       auto issue_s = [&](int t, int slot) {
@@ -408,8 +418,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // channel slice kk: sub-tile kk / 4 (64 channels each), 32 bytes per 16 channels inside the 128-byte row
           const uint64_t da = make_smem_desc_sw128(a0 + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(b0 + (kk >> 2) * (KV_BYTES / 2) + (kk & 3) * 32, 16, 1024);
-          if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
-          else umma_ss(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
+          if (issuer) {
+            if constexpr (NCTA == 2) umma_ss_2sm(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, da, db, idesc_s, kk != 0 ? 1u : 0u);
+          }
         }
       };
       auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
@@ -423,8 +435,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // 16 keys = 16 rows of 128 bytes; pair: this CTA's 64 channels are ONE swizzle atom (no leading-dim stride)
           const uint64_t db = make_smem_desc_sw128(b0 + kk * 2048, HALF_BYTES, 1024);
           const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-          if constexpr (NCTA == 2) umma_ts_2sm(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
-          else umma_ts(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
+          if (issuer) {
+            if constexpr (NCTA == 2) umma_ts_2sm(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
+            else umma_ts(d_tmem, a_tmem + kk * 8, db, idesc_o, acc);
+          }
         }
       };
       // Ring items in load order -> item i lives in slot i % KV_SLOTS, phase (i / KV_SLOTS) & 1.
@@ -471,7 +485,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int n_my = !MULTI ? 1 : (w0 < p.n_items ? (p.n_items - w0 + w_step - 1) / w_step : 0);   // work items of this CTA
 #pragma unroll 1
         for (int n_it = 0; n_it < n_my; ++n_it) {
-          const bool prof_cta = PROF && blockIdx.x == 0;
+          const bool prof_cta = PROF && blockIdx.x == 0 && issuer;
           (void)prof_cta;
           role_wait(q_full, n_it & 1);
           ATTN_STAMP(0, 20);   // Q landed
@@ -533,7 +547,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       } else {
         // round-1 order  PV0(j) S0(j+1) PV1(j) S1(j+1)  (P_t aliases S_t); launched non-persistently (one work item)
-        const bool prof_cta = PROF && blockIdx.x == 0;
+        const bool prof_cta = PROF && blockIdx.x == 0 && issuer;
         (void)prof_cta;
         role_wait(q_full, 0);
         wait_item(0);
