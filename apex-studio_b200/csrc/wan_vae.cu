@@ -1,7 +1,7 @@
 // b200_wan_vae_decode: the whole Wan 3D-VAE decoder (post_quant_conv + WanDecoder3d, non-residual, all frames of one
 // latent tile) issued from ONE C call -- the launch sequence of AutoencoderKLWan._decode / WanDecoder3d.forward
 // (vae/wan/model.py:1333-1375, 972-1021; WanResidualBlock :389-441, WanAttentionBlock :461-490, WanResample :291-353)
-// on the kernels of this library (conv.cu, vae_ops.cu, linear.cu).  ~197 launches per 32 x 32 x 21 tile, no allocation:
+// on the kernels of this library (conv.cu, vae_ops.cu, linear.cu).  ~130 launches per 32 x 32 x 21 tile (197 before conv1 + norm2 became one kernel and the mid-attention projections ran once over all frames), no allocation:
 // every intermediate lives in a caller-supplied workspace, handed out by a two-region ping-pong arena (a block reads its
 // input from one region and builds its output + temporaries in the other), sized by b200_wan_vae_decode_workspace.
 //

@@ -439,10 +439,13 @@ class AutoencoderKLWan:
         return out
 
     def _tile_launches(self, T: int) -> int:
-        """kernels b200_wan_vae_decode enqueues for a T-frame tile: post_quant + conv_in + conv_out + norm_out (4), 14 residual
-        blocks x 4 (+1 per shortcut), the mid attention (1 + 6 per frame), 3 upsamplers x 2 (+1 time_conv each when T > 1)"""
+        """kernels b200_wan_vae_decode enqueues for a T-frame tile: post_quant + conv_in + conv_out + norm_out (4), the residual
+        blocks (norm1, conv1, norm2, conv2; 3 where conv1 + norm2 are one kernel; +1 per shortcut), the mid attention (norm,
+        q|k, V^T, output projection + 3 per frame), 3 upsamplers x 2 (+1 time_conv each when T > 1)"""
         w = self.w
-        n = 4 + 14 * 4 + sum(1 for k in w if k.endswith("conv_shortcut.weight")) + 1 + 6 * T + 3 * 2
+        res = [k for k in w if k.endswith(".conv1.bias") and ".resnets." in k]
+        n = 4 + sum(3 if conv_norm_fusable(w[k].numel()) else 4 for k in res)
+        n += sum(1 for k in w if k.endswith("conv_shortcut.weight")) + 4 + 3 * T + 3 * 2
         if T > 1:
             n += sum(1 for t in self.temporal_upsample if t)
         return n
