@@ -39,6 +39,19 @@
 // SLOWER (1029-1080 TFLOP/s): the remote arrives and multicast commits add ~400 cycles to hand-overs that sit on the
 // critical path of this kernel (unlike the GEMM, where the pair gained 10 %), so single CTAs stay the default.
 //
+// LAUNCH FORMS of the decoupled 1-CTA pipeline (host side of attn_fwd_impl; work item = (256 query rows, head, batch)):
+//   long key sequences  (> MULTI_MAX_KV_TILES key tiles; Wan self-attention: 591): one work item per CTA, 5-slot K/V ring,
+//                        epilogue = 32-byte direct stores.  The per-CTA prologue is amortised; the item loops fold away (MULTI = false).
+//   mid                 (<= 128 key tiles; FLUX / QwenImage joint attention: 36 / 68): PERSISTENT grid, one CTA per SM walks the
+//                        items: barriers, TMEM and descriptors are set up once; the next item's Q / K_0 / K_1 loads and its S_0(0)
+//                        MMAs run under the current epilogue ("Q empty" after the item's last S MMA, "O free" before its first PV).
+//   short               (<= STAGE_MAX_KV_TILES; Wan cross-attention: 4): persistent + STAGED epilogue -- O goes through shared
+//                        memory (two 128B-swizzled 4 KB boxes per softmax warp) and out by TMA bulk stores; the 64 KB staging area
+//                        replaces two ring slots.  One thread owns one output row, so direct stores touch 32 lines per instruction:
+//                        5,000-7,000 cycles per item, a third of a 4-key-tile item (profiles/r02_attn_cross_timeline.log).
+//   Sequence-parallel scatter epilogues (b200_attn_fwd_scatter, b200_attn_fwd_scatter_joint) use the direct-store form.
+//   Measured (same box): Wan cross-attention 650 -> 1080 TFLOP/s (cuDNN 1100-1200), self-attention 1337 -> 1365-1377 (cuDNN 1366-1388).
+//
 // Replaces attention_register.call(q, k, v) -- attention/functions.py:84 (`sdpa` :338-377 is the gold
 // backend) as called by transformer/wan/base/attention.py:397.
 #include "host_util.cuh"

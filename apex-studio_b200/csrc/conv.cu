@@ -10,6 +10,9 @@
 // The A operand of tap (kt,kh,kw) is a shifted [BH x BW x BK] window of x, fetched by ONE 4-D TMA box whose
 // out-of-bounds elements (halo, causal left pad) are zero-filled by the TMA unit -- no im2col buffer, no padded copy.
 // The B operand is the [BN x BK] slice of the tap's weight matrix (host layout [tap][C_out][C_in]).
+// Forms (round 2): KC channel chunks per pipeline stage (KC = 3 puts all 96 channels of a tap behind ONE barrier round trip);
+// 32-byte epilogue loads / stores; a fused consumer epilogue (RMS-norm + SiLU of the conv output: b200_conv3d_cl_norm_silu);
+// an opt-in temporally blocked kernel (conv3d_tb_kernel, B200_CONV_TB) kept with its measurements.
 // Warp roles / pipeline are those of linear.cu: warp 0 TMA, warp 1 MMA (fp32 accumulators in TMEM, two buffers),
 // warps 2-5 epilogue (bias, optional residual add, bf16 channels-last store, or planar store for conv_out, or the
 // 2x temporal interleave of upsample3d, vae/wan/model.py:332-334).
