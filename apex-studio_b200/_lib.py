@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p]),
     "b200_attn_fwd_prof": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p, _i, _p]),
     "b200_linear": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _p]),
+    "b200_linear_normw": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i64, _i64, _i64, _p]),
+    "b200_attn_fwd_qnorm": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i] + [_i64] * 12 + [_f, _p, _i, _i, _f, _p]),
     "b200_layernorm_modulate": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i64, _i64, _f, _p]),
     "b200_rmsnorm_rope": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p]),
     "b200_rmsnorm_rope_batched": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _i, _i64, _i64, _p]),

@@ -123,6 +123,12 @@ struct Params {
   // rows are token-sharded as above.  rep_first: the replicated rows come first (Flux / QwenImage), else last (HunyuanVideo-1.5).
   // Every peer's buffer is laid out like its local joint sequence: [rep_rows + rows_per_rank, H_total * 128] in the same order.
   int rep_rows, rep_first;
+  // b200_attn_fwd_qnorm: the RMS-norm of q over all H * 128 channels of a token, folded into the logits: row r of every head is
+  // scaled by rstd[r] = bf16(rsqrt(sum_i q_rowsumsq[(batch * Sq + r) * q_parts + i] * q_inv_dim + q_eps)) (the per-channel norm
+  // weight was applied by the projection's epilogue, b200_linear_normw).  NULL = plain attention.
+  const float* q_rowsumsq;
+  int q_parts;
+  float q_inv_dim, q_eps;
   long long* prof;    // PROF kernels only: [steps][16] SM-clock timestamps of CTA (0,0,0) (b200_attn_fwd_prof)
   int prof_steps;
 };
@@ -608,7 +614,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t o_addr = tmem_base + lane_base + (t ? O_COL1 : O_COL0);
     const uint32_t p_full_remote = NCTA == 2 ? mapa_u32(&p_full[t], 0) : 0u;
     const uint32_t s_free_remote = NCTA == 2 ? mapa_u32(s_free, 0) : 0u;
-    const float sl2 = p.scale_log2;
     const uint32_t o_free_remote = NCTA == 2 ? mapa_u32(&o_free[t], 0) : 0u;
     uint32_t n_steps = 0;  // key-tile steps of the work items already done by this CTA: parity base of s_full / o_done
     bool first_item = true;
@@ -618,6 +623,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t step_base = MULTI ? n_steps : 0u;
     const bool prof_cta = PROF && blockIdx.x == 0;
     (void)prof_cta;
+    float sl2 = p.scale_log2;
+    if (p.q_rowsumsq != nullptr) {
+      // logits of this thread's query row carry the row's RMS-norm factor (every head of a token shares it)
+      const Item wq = decode_item(it);
+      const int qrow = wq.row_base + t * TILE_ROW_STEP + quad * 32 + lane;
+      float ss = 0.f;
+      if (qrow < p.Sq) {
+        const float* part = p.q_rowsumsq + (static_cast<int64_t>(wq.batch) * p.Sq + qrow) * p.q_parts;
+        for (int i = 0; i < p.q_parts; ++i) ss += __ldg(part + i);
+      }
+      sl2 *= __bfloat162float(__float2bfloat16(rsqrtf(ss * p.q_inv_dim + p.q_eps)));   // y.to(dtype=x.dtype), efficiency/mod.py:24-35
+    }
     float m = -INFINITY;  // running max of s * scale_log2 actually used for P
     float l = 0.f;        // running sum of P
     // One key tile.  MASKED is a compile-time flag: only the LAST tile can be partial (Sk % 128 != 0); written as a run-time
@@ -865,7 +882,8 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                          float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
-                         long long* prof = nullptr, int prof_steps = 0, int rep_rows = 0, int rep_first = 0);
+                         long long* prof = nullptr, int prof_steps = 0, int rep_rows = 0, int rep_first = 0,
+                         const float* q_rowsumsq = nullptr, int q_parts = 0, float q_inv_dim = 0.f, float q_eps = 0.f);
 
 // Diagnostics: b200_attn_fwd with SM-clock timestamps of the softmax / MMA hand-offs of CTA (0,0,0) written to
 // prof[prof_steps][32] (device memory): columns 0-4 softmax tile 0 (S seen ready, S in registers, row max done, P stores
@@ -885,6 +903,16 @@ extern "C" int b200_attn_fwd(const void* q, const void* k, const void* v, void* 
                              float scale, void* stream) {
   return attn_fwd_impl(q, k, v, o, B, H, Sq, Sk, D, q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss, o_sb, o_sh, o_ss,
                        scale, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int b200_attn_fwd_qnorm(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                                   int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                                   int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                                   float scale, const float* q_rowsumsq, int q_parts, int q_norm_dim, float q_eps, void* stream) {
+  if (!q_rowsumsq || q_parts <= 0 || q_norm_dim <= 0) return B200_ERR_ARG;
+  return attn_fwd_impl(q, k, v, o, B, H, Sq, Sk, D, q_sb, q_sh, q_ss, k_sb, k_sh, k_ss, v_sb, v_sh, v_ss, o_sb, o_sh, o_ss,
+                       scale, nullptr, 0, 0, 0, stream, nullptr, 0, 0, 0, q_rowsumsq, q_parts, 1.0f / static_cast<float>(q_norm_dim),
+                       q_eps);
 }
 
 extern "C" int b200_attn_fwd_scatter_joint(const void* q, const void* k, const void* v, int H, int Sq, int Sk, int D,
@@ -911,7 +939,8 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
                          int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
                          int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
                          float scale, void* const* o_peers, int n_peers, int rows_per_rank, int head_off, void* stream,
-                         long long* prof, int prof_steps, int rep_rows, int rep_first) {
+                         long long* prof, int prof_steps, int rep_rows, int rep_first, const float* q_rowsumsq, int q_parts,
+                         float q_inv_dim, float q_eps) {
   using namespace b200;
   using namespace b200::attn;
   if (!q || !k || !v || !o) return B200_ERR_ARG;
@@ -998,6 +1027,10 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, i
   p.head_off = head_off;
   p.rep_rows = rep_rows;
   p.rep_first = rep_first;
+  p.q_rowsumsq = q_rowsumsq;
+  p.q_parts = q_parts;
+  p.q_inv_dim = q_inv_dim;
+  p.q_eps = q_eps;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = (o_peers && i < n_peers) ? o_peers[i] : nullptr;
   p.prof = prof;
   p.prof_steps = prof_steps;

@@ -76,6 +76,11 @@ struct Params {
   int tiles_m, tiles_n;
   int tma_store; // 1: bf16 output written through shared memory + TMA (128-byte lines) instead of 16-byte stores per lane
   int c_vec32;   // rows of C are 32-byte aligned (bf16 outputs): the direct epilogues use 32-byte loads / stores
+  // B200_EPI_NORMW (the RMS-norm of the cross-attention query folded into its projection, attention.py:345-370): the epilogue
+  // stores bf16(q * w[n]) with q = bf16(acc + bias) and writes sum_n q^2 of every row and column tile to row_sumsq[row, part];
+  // the attention kernel multiplies its logits by rsqrt(mean + eps) of the row (b200_attn_fwd_qnorm).
+  float* row_sumsq;
+  int n_parts;
   int group_m;   // row-tiles per rasterisation group (the A rows of a group stay in L2 while its n-tiles are swept)
   int panel_n;   // column-tiles per panel: the W panel (panel_n x BN x K) stays in L2 while ALL row groups sweep it
 };
@@ -282,6 +287,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // and one elected lane issues a bulk tensor store of full 128-byte lines; the M / N tails are clipped by the TMA unit.
         uint8_t* my_stage = epi_stage + (warp - 2) * 2 * EPI_BOX_BYTES;
         const int row_base = row - lane;
+        float ss = 0.f;   // B200_EPI_NORMW: sum of squares of this row over the tile's columns
 #pragma unroll 1
         for (int c = 0; c < BN_T / 64; ++c) {
           const int col0 = (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn) * BN_T + c * 64;
@@ -317,7 +323,27 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
             }
           }
-          if (p.epi == B200_EPI_GELU_TANH) {
+          if (p.epi == B200_EPI_NORMW) {
+            const bool full64 = (col0 + 64 <= p.N);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float wv[8];
+              if (full64) {
+                const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.gate + col0) + q4);
+                wv[0] = bf16_lo(g.x); wv[1] = bf16_hi(g.x); wv[2] = bf16_lo(g.y); wv[3] = bf16_hi(g.y);
+                wv[4] = bf16_lo(g.z); wv[5] = bf16_hi(g.z); wv[6] = bf16_lo(g.w); wv[7] = bf16_hi(g.w);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wv[j] = (col0 + q4 * 8 + j < p.N) ? __bfloat162float(p.gate[col0 + q4 * 8 + j]) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float q = __bfloat162float(__float2bfloat16(v[q4 * 8 + j]));   // the projection output as the reference stores it
+                if (full64 || col0 + q4 * 8 + j < p.N) ss += q * q;
+                v[q4 * 8 + j] = q * wv[j];
+              }
+            }
+          } else if (p.epi == B200_EPI_GELU_TANH) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
           } else if (p.epi == B200_EPI_SILU) {
@@ -346,6 +372,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_store_commit();
           }
         }
+        if (p.epi == B200_EPI_NORMW && row_ok)
+          p.row_sumsq[static_cast<int64_t>(row) * p.n_parts + (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn)] = ss;
         continue;   // next half / tile
       }
 #pragma unroll 1
@@ -506,14 +534,32 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }  // namespace linear
 }  // namespace b200
 
+static int linear_impl(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N, int K,
+                       int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream, float* row_sumsq, int* n_parts_out);
+
 extern "C" int b200_linear(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N,
                            int K, int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream) {
+  if ((epilogue & ~B200_EPI_ROW_BIAS) == B200_EPI_NORMW) return B200_ERR_ARG;   // needs b200_linear_normw (row_sumsq output)
+  return linear_impl(A, W, bias, C, gate, M, N, K, lda, ldw, ldc, epilogue, stream, nullptr, nullptr);
+}
+
+extern "C" int b200_linear_normw(const void* A, const void* W, const void* bias, const void* norm_w, void* C, float* row_sumsq,
+                                 int row_sumsq_capacity, int* n_parts, int M, int N, int K, int64_t lda, int64_t ldw,
+                                 int64_t ldc, void* stream) {
+  if (!norm_w || !row_sumsq || !n_parts) return B200_ERR_ARG;
+  if (row_sumsq_capacity < (N + 63) / 64) return B200_ERR_SHAPE;   // parts per row for the narrowest column tile (64)
+  return linear_impl(A, W, bias, C, norm_w, M, N, K, lda, ldw, ldc, B200_EPI_NORMW, stream, row_sumsq, n_parts);
+}
+
+static int linear_impl(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N, int K,
+                       int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream, float* row_sumsq, int* n_parts_out) {
   using namespace b200;
   using namespace b200::linear;
   if (!A || !W || !C) return B200_ERR_ARG;
   const int bias_row = (epilogue & B200_EPI_ROW_BIAS) ? 1 : 0;
   epilogue &= ~B200_EPI_ROW_BIAS;
-  if (epilogue < 0 || epilogue > 5) return B200_ERR_ARG;
+  if (epilogue < 0 || epilogue > 6) return B200_ERR_ARG;
+  if (epilogue == B200_EPI_NORMW && (!gate || !row_sumsq || bias_row || N < 64)) return B200_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0) return B200_ERR_SHAPE;
   if ((K % 8) || (lda % 8) || (ldw % 8)) return B200_ERR_ALIGN;
   if (epilogue == B200_EPI_BIAS_F32 ? (ldc % 4) : (ldc % 8)) return B200_ERR_ALIGN;
@@ -584,7 +630,8 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
     const char* ev = getenv("B200_LINEAR_TMA_STORE");
     tma_store_mode = ev ? (ev[0] == '1' ? 1 : 0) : 1;
   }
-  const bool use_tma_store = tma_store_mode == 1 && epilogue != B200_EPI_GATE_RES && epilogue != B200_EPI_BIAS_F32 && N >= 64;
+  const bool use_tma_store = (tma_store_mode == 1 || epilogue == B200_EPI_NORMW) && epilogue != B200_EPI_GATE_RES &&
+                             epilogue != B200_EPI_BIAS_F32 && N >= 64;   // NORMW lives in the staged epilogue only
   CUtensorMap tmC;
   memset(&tmC, 0, sizeof(tmC));
   if (use_tma_store) {
@@ -604,6 +651,9 @@ extern "C" int b200_linear(const void* A, const void* W, const void* bias, void*
   p.ldc = ldc;
   p.epi = epilogue;
   p.bias_row = bias_row;
+  p.row_sumsq = row_sumsq;
+  p.n_parts = (N + bn - 1) / bn;
+  if (n_parts_out) *n_parts_out = p.n_parts;
   p.tiles_m = (M + rows_per_cta * ncta - 1) / (rows_per_cta * ncta);
   p.tiles_n = (N + bn - 1) / bn;
   if (use_quad) p.tiles_n = (p.tiles_n + 1) / 2;      // column tile PAIRS

@@ -53,11 +53,14 @@ def _count(n: int = 1) -> None:
 # attention core
 # ---------------------------------------------------------------------------------------------------
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, q_norm: Optional[tuple] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v for q [B,H,Sq,128], k/v [B,H,Sk,128] (any strides with a contiguous last dim).
 
     Returns [B,H,Sq,128] as a transposed view of a [B,Sq,H,128] buffer -- the layout the caller wants next
     (reference: attention.py:397-401 immediately does ``.transpose(1, 2).flatten(2, 3)``).
+
+    ``q_norm = (row_sumsq, n_parts, dim, eps)`` from :func:`linear_normw`: the RMS-norm of q over all heads' channels is
+    applied to the logits row by row (``b200_attn_fwd_qnorm``) instead of to q in a separate pass.
     """
     for name, t in (("q", q), ("k", k), ("v", v)):
         _require_cuda_bf16(name, t)
@@ -90,13 +93,49 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: 
             raise ValueError("out needs 16-byte aligned strides and base address")
     scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
     lib = _lib.load()
-    rc = lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Sk, D,
-                           q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-                           v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2),
-                           scale, _stream())
-    _lib.check(rc, "b200_attn_fwd")
+    strides = (q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+               v.stride(0), v.stride(1), v.stride(2), out.stride(0), out.stride(1), out.stride(2))
+    if q_norm is not None:
+        sumsq, n_parts, dim, eps = q_norm
+        if sumsq.dtype != torch.float32 or not sumsq.is_cuda or not sumsq.is_contiguous() or sumsq.numel() < B * Sq * n_parts:
+            raise ValueError("q_norm row_sumsq must be a contiguous fp32 CUDA tensor of at least B * Sq * n_parts elements")
+        rc = lib.b200_attn_fwd_qnorm(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Sk, D, *strides, scale,
+                                     sumsq.data_ptr(), int(n_parts), int(dim), float(eps), _stream())
+        _lib.check(rc, "b200_attn_fwd_qnorm")
+    else:
+        rc = lib.b200_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Sq, Sk, D, *strides, scale, _stream())
+        _lib.check(rc, "b200_attn_fwd")
     _count()
     return out
+
+
+def linear_normw(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], norm_weight: torch.Tensor, out: torch.Tensor,
+                 row_sumsq: torch.Tensor) -> int:
+    """out = bf16(q * norm_weight) with q = bf16(x @ weight^T + bias); ``row_sumsq`` (flat fp32, >= M * ceil(N / 64) elements)
+    receives the sums of q^2 per row and column tile as [M, n_parts].  Returns n_parts, the number of parts per row the kernel
+    wrote (pass it on as ``q_norm`` to :func:`attention`).  The RMS-norm of the Wan cross-attention query folded into its
+    projection (attention.py:345-370)."""
+    for name, t in (("x", x), ("weight", weight), ("norm_weight", norm_weight), ("out", out)):
+        _require_cuda_bf16(name, t)
+    if x.dim() != 2 or x.stride(1) != 1 or weight.stride(1) != 1 or out.dim() != 2 or out.stride(1) != 1:
+        raise ValueError("x, weight and out must be 2-D with a contiguous last dim")
+    M, K = x.shape
+    N = weight.shape[0]
+    if tuple(out.shape) != (M, N) or norm_weight.numel() != N or not norm_weight.is_contiguous():
+        raise ValueError("shape mismatch")
+    cap = row_sumsq.numel() // M
+    if row_sumsq.dtype != torch.float32 or not row_sumsq.is_cuda or not row_sumsq.is_contiguous() or cap < (N + 63) // 64:
+        raise ValueError("row_sumsq must be a contiguous fp32 CUDA tensor of at least M * ceil(N / 64) elements")
+    import ctypes
+
+    n_parts = ctypes.c_int(0)
+    lib = _lib.load()
+    rc = lib.b200_linear_normw(x.data_ptr(), weight.data_ptr(), _ptr(bias), norm_weight.data_ptr(), out.data_ptr(),
+                               row_sumsq.data_ptr(), int(cap), ctypes.byref(n_parts), M, N, K, x.stride(0), weight.stride(0),
+                               out.stride(0), _stream())
+    _lib.check(rc, "b200_linear_normw")
+    _count()
+    return n_parts.value
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -8,12 +8,16 @@ engine's denoise loop (engine/wan/shared/__init__.py:548-563) can call it unchan
 ``TRANSFORMERS_REGISTRY["wan.b200"]`` (INTEGRATION.md).
 
 What runs where: every FLOP of the 40 blocks, the embedders, the patch embedding and the output head goes
-through libapex_b200.so (``ops``): 13 kernel launches per block --
+through libapex_b200.so (``ops``): 12 kernel launches per block --
 
     layernorm_modulate -> linear(QKV fused) -> rmsnorm_rope(q and k, ONE launch) -> attention
       -> linear(to_out, epilogue h += gate * y)
-    layernorm(affine)  -> linear(q) -> rmsnorm(q) -> attention -> linear(to_out, epilogue h += y)
+    layernorm(affine)  -> linear(q, epilogue * norm_q weight + row sums of squares) -> attention(logits * rstd of the row)
+      -> linear(to_out, epilogue h += y)
     layernorm_modulate -> linear(ffn.0, epilogue gelu-tanh) -> linear(ffn.2, epilogue h += gate * y)
+
+(the cross-attention's norm_q has no kernel of its own: its per-channel weight is applied by the projection's epilogue, its
+row factor rsqrt(mean(q^2) + eps) by the attention kernel on the logits -- ``fuse_cross_q_norm``; 13 launches without it)
 
 plus TWO launches per forward for the text side of every layer's cross-attention: the to_k|to_v projections of all layers
 are one GEMM over the stacked weights ([L_text, 5120] x [5120, layers * 10240]) and the norm_k of all layers one batched
@@ -25,6 +29,8 @@ are reused by all layers (HBM layout: token-major [S, channels] bf16; q|k|v as c
 [S, 3*dim] buffer so the attention kernel reads them through strided TMA maps without a transpose).
 """
 from __future__ import annotations
+
+import os
 
 import math
 from dataclasses import dataclass, field
@@ -72,6 +78,8 @@ class _Workspace:
         self.attn = torch.empty(tokens, d, dtype=bf, device=device)
         self.ffn = torch.empty(tokens, cfg.ffn_dim, dtype=bf, device=device)
         self.kv_ctx = torch.empty(ctx_tokens, cfg.num_layers * 2 * d, dtype=bf, device=device)   # K|V of EVERY layer's cross-attention
+        # per-row, per-column-tile sums of squares of the cross-attention query (ops.linear_normw -> ops.attention(q_norm=...))
+        self.q_sumsq = torch.empty(tokens * ((d + 63) // 64), dtype=torch.float32, device=device)
 
 
 class WanTransformer3DModel(LoraHostMixin):
@@ -91,6 +99,9 @@ class WanTransformer3DModel(LoraHostMixin):
         self.device = None
         self._use_graph = False
         self._graphs: Dict[Tuple, object] = {}
+        #: norm_q of the cross-attention folded into its projection and the attention logits (B200_WAN_FUSE_Q_NORM=0: the
+        #: three-kernel form projection -> RMS-norm -> attention, the A/B partner)
+        self.fuse_cross_q_norm = os.environ.get("B200_WAN_FUSE_Q_NORM", "1") != "0"
 
     # ------------------------------------------------------------------------------------ weights
     @classmethod
@@ -334,14 +345,23 @@ class WanTransformer3DModel(LoraHostMixin):
             xn = ws.norm
         else:
             xn = h
-        q2 = ops.linear(xn, w[p + ".attn2.to_q.weight"], w[p + ".attn2.to_q.bias"], out=ws.attn)
-        ops.rmsnorm_rope_(q2, w[p + ".attn2.norm_q.weight"], None, heads, eps)
+        fuse_q_norm = self.fuse_cross_q_norm and d >= 64
+        if fuse_q_norm:
+            # norm_q folded into the projection (per-channel weight in the GEMM epilogue, row statistics on the side) and into the
+            # attention logits (row factor): no separate pass over q -- 12 launches per block
+            q2 = ws.attn
+            q_parts = ops.linear_normw(xn, w[p + ".attn2.to_q.weight"], w[p + ".attn2.to_q.bias"], w[p + ".attn2.norm_q.weight"], q2,
+                                       ws.q_sumsq)
+        else:
+            q2 = ops.linear(xn, w[p + ".attn2.to_q.weight"], w[p + ".attn2.to_q.bias"], out=ws.attn)
+            ops.rmsnorm_rope_(q2, w[p + ".attn2.norm_q.weight"], None, heads, eps)
         L = ctx.shape[0]
         # K | V of this layer's cross-attention: column block i of ws.kv_ctx, projected + normalised for ALL layers by
         # ``text_kv`` at the top of the forward
         k2, v2 = ws.kv_ctx[:, i * 2 * d:i * 2 * d + d], ws.kv_ctx[:, i * 2 * d + d:(i + 1) * 2 * d]
         o2 = ws.norm  # norm output is dead once q2 exists
-        ops.attention(as4(q2, S), as4(k2, L), as4(v2, L), out=as4(o2, S))
+        ops.attention(as4(q2, S), as4(k2, L), as4(v2, L), out=as4(o2, S),
+                      q_norm=(ws.q_sumsq, q_parts, d, eps) if fuse_q_norm else None)
         ops.linear(o2, w[p + ".attn2.to_out.0.weight"], w[p + ".attn2.to_out.0.bias"], epilogue=ops.EPI_GATE_RES,
                    out=h, gate=None)
 

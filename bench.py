@@ -222,15 +222,15 @@ def run_b200_arm(args):
     attn_events = []
     orig_attention = ops.attention
 
-    def timed_attention(q, k, v, softmax_scale=None, out=None):
+    def timed_attention(q, k, v, softmax_scale=None, out=None, **kw):
         if q.shape[2] == k.shape[2] and q.shape[2] >= 4096 and timed_attention.on:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            r = orig_attention(q, k, v, softmax_scale, out)
+            r = orig_attention(q, k, v, softmax_scale, out, **kw)
             e.record()
             attn_events.append((s, e, q.shape[1], q.shape[2]))
             return r
-        return orig_attention(q, k, v, softmax_scale, out)
+        return orig_attention(q, k, v, softmax_scale, out, **kw)
 
     timed_attention.on = False
     ops.attention = timed_attention

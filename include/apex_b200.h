@@ -51,6 +51,17 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, i
                   float scale, void* stream);
 
 /*
+ * b200_attn_fwd for a query whose RMS-norm over all H * 128 channels of a token (norm_q of the Wan cross-attention,
+ * attention.py:345-370 / efficiency/mod.py:24-35) is folded in: the logits of query row r are multiplied by
+ * rstd[r] = bf16(rsqrt(sum_i q_rowsumsq[(b * Sq + r) * q_parts + i] / q_norm_dim + q_eps)); q itself is the projection output
+ * already multiplied by the norm weight (b200_linear_normw, which also writes q_rowsumsq).
+ */
+int b200_attn_fwd_qnorm(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk, int D,
+                        int64_t q_sb, int64_t q_sh, int64_t q_ss, int64_t k_sb, int64_t k_sh, int64_t k_ss,
+                        int64_t v_sb, int64_t v_sh, int64_t v_ss, int64_t o_sb, int64_t o_sh, int64_t o_ss,
+                        float scale, const float* q_rowsumsq, int q_parts, int q_norm_dim, float q_eps, void* stream);
+
+/*
  * Linear layer with fused epilogue: C = epilogue(A @ W^T + bias).
  *   A: [M,K] row stride lda;  W: [N,K] row stride ldw (nn.Linear weight layout);  bias: [N] or NULL.
  * epilogue:
@@ -67,11 +78,24 @@ int b200_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, i
 #define B200_EPI_BIAS_F32 3
 #define B200_EPI_SILU 4     /* C = silu(acc + bias): FeedForward("linear-silu"), hunyuanvideo15/base/model.py:545-550 */
 #define B200_EPI_GELU_ERF 5 /* C = gelu(acc + bias), exact erf form: nn.GELU(), hunyuanvideo15/base/model.py:571,589 */
+#define B200_EPI_NORMW 6    /* b200_linear_normw only: C = bf16(acc + bias) * w[n], row sums of squares on the side */
 /* OR-ed into `epilogue`: bias is indexed by ROW ([M]) instead of by column -- used for transposed projections
  * (V^T = W_v x^T + b_v of the VAE mid-block attention, vae/wan/model.py:470-478). */
 #define B200_EPI_ROW_BIAS 16
 int b200_linear(const void* A, const void* W, const void* bias, void* C, const void* gate, int M, int N, int K,
                 int64_t lda, int64_t ldw, int64_t ldc, int epilogue, void* stream);
+
+/*
+ * The cross-attention query projection with its RMS-norm folded in (attention.py:345-370: q = norm_q(to_q(x)) with the norm
+ * taken over ALL heads' channels): C = bf16(q * norm_w[n]) with q = bf16(A W^T + bias) as the reference stores it, and
+ * row_sumsq[row * n_parts + part] = sum of q^2 over the columns of column tile `part` (*n_parts tiles per row, decided by the
+ * kernel form; row_sumsq must hold M * row_sumsq_capacity floats with row_sumsq_capacity >= ceil(N / 64)).  The row's
+ * rsqrt(mean(q^2) + eps) is applied to the attention logits by b200_attn_fwd_qnorm: one kernel launch and one read + write
+ * pass over q less than projection -> b200_rmsnorm_rope, and one rounding of q less (q * rstd is never rounded to bf16).
+ */
+int b200_linear_normw(const void* A, const void* W, const void* bias, const void* norm_w, void* C, float* row_sumsq,
+                      int row_sumsq_capacity, int* n_parts, int M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc,
+                      void* stream);
 
 /*
  * y = LayerNorm_fp32(x, eps, no affine) * (1 + scale) + shift      (adaLN modulate)

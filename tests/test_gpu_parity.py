@@ -298,7 +298,8 @@ def test_wan_forward_cuda_graph_replay_is_bit_identical():
     model(*a)
     per_forward = ops.launch_count - n0
     L = cfg["num_layers"]
-    assert per_forward == 13 * L + 2 + 8, per_forward        # 13 per block, 2 for all layers' text K|V, 8 embedders / patchify / head
+    per_block = 12 if model.fuse_cross_q_norm else 13         # norm_q of the cross-attention folded into projection + logits
+    assert per_forward == per_block * L + 2 + 8, per_forward  # + 2 for all layers' text K|V, 8 embedders / patchify / head
     model.enable_cuda_graph()
     ga = model(*a)[0]
     gb = model(*b)[0]
@@ -400,6 +401,44 @@ def test_scatter_kernels_addressing_on_one_gpu(ops):
         rows = ref_o[0, :, d * (S // P):(d + 1) * (S // P)]                      # [hp, S/P, hd]
         assert torch.equal(obufs[d][:, 2 * hd:], rows.transpose(0, 1).reshape(S // P, hp * hd))
         assert obufs[d][:, :2 * hd].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rows,heads,L", [(333, 2, 77), (1000, 40, 512), (4100, 8, 130)])
+def test_cross_attention_q_norm_folded_into_projection_and_logits(ops, rows, heads, L):
+    """b200_linear_normw + b200_attn_fwd_qnorm (norm_q of the Wan cross-attention without a kernel of its own) vs the
+    three-kernel form projection -> RMS-norm -> attention and vs fp32 math of attention.py:345-370."""
+    torch.manual_seed(rows + heads)
+    dim = heads * 128
+    x = torch.randn(rows, 256, device=DEV).bfloat16()
+    wq = (torch.randn(dim, 256, device=DEV) * 0.08).bfloat16()
+    bq = (torch.randn(dim, device=DEV) * 0.1).bfloat16()
+    nw = (1 + 0.2 * torch.randn(dim, device=DEV)).bfloat16()
+    k = torch.randn(L, dim, device=DEV).bfloat16()
+    v = torch.randn(L, dim, device=DEV).bfloat16()
+    as4 = lambda t, n: t.view(1, n, heads, 128).transpose(1, 2)
+    # three kernels
+    q3 = ops.linear(x, wq, bq)
+    ops.rmsnorm_rope_(q3, nw, None, heads, 1e-6)
+    o3 = torch.empty(rows, dim, device=DEV, dtype=torch.bfloat16)
+    ops.attention(as4(q3, rows), as4(k, L), as4(v, L), out=as4(o3, rows))
+    # folded
+    q2 = torch.empty(rows, dim, device=DEV, dtype=torch.bfloat16)
+    sumsq = torch.empty(rows * (dim // 64), device=DEV, dtype=torch.float32)
+    parts = ops.linear_normw(x, wq, bq, nw, q2, sumsq)
+    assert 1 <= parts <= dim // 64
+    qpre = (x.float() @ wq.float().t() + bq.float()).bfloat16().float()
+    got_ss = sumsq[:rows * parts].view(rows, parts).sum(1)
+    assert rel_l2(got_ss, (qpre * qpre).sum(1)) <= 1e-5
+    assert rel_l2(q2, qpre * nw.float()) <= 3e-3
+    o2 = torch.empty(rows, dim, device=DEV, dtype=torch.bfloat16)
+    ops.attention(as4(q2, rows), as4(k, L), as4(v, L), out=as4(o2, rows), q_norm=(sumsq, parts, dim, 1e-6))
+    # fp32 math of the reference sequence
+    qn = qpre * torch.rsqrt((qpre * qpre).mean(1, keepdim=True) + 1e-6) * nw.float()
+    exact = wan_dit.sdpa_fp32_math(as4(qn, rows).cpu(), as4(k.float(), L).cpu(), as4(v.float(), L).cpu())
+    exact = exact.transpose(1, 2).reshape(rows, dim)
+    e3, e2 = rel_l2(o3, exact), rel_l2(o2, exact)
+    assert e2 <= max(5e-3, 1.2 * e3), (e2, e3)           # not worse than the three-kernel form (it rounds q once less)
+    assert rel_l2(o2, o3) <= 8e-3
 
 
 # ------------------------------------------------------------------------------------------------ composite C entry points
