@@ -69,6 +69,17 @@ def test_argument_validation_needs_no_gpu():
     assert lib.b200_linear(None, None, None, None, None, 1, 1, 8, 8, 8, 8, 0, None) == -6
     assert lib.b200_attn_fwd(1, 1, 1, 16, 1, 1, 8, 8, 64, *([8] * 12), 1.0, None) == -1  # head_dim 64
     assert lib.b200_layernorm_modulate(16, 16, None, None, None, None, 4, 12, 16, 16, 0, 1e-6, None) == -2
+    # round-2 entry points: the NORMW epilogue only through b200_linear_normw (it needs the row_sumsq output), which checks its
+    # extra operands and the capacity of the partial-sum buffer; the q-norm attention needs the partial sums; the fused
+    # conv + norm epilogue rejects channel counts that span two N tiles; the joint scatter checks its peer table
+    assert lib.b200_linear(16, 16, None, 16, 16, 64, 64, 64, 64, 64, 64, 6, None) == -6
+    assert lib.b200_linear_normw(16, 16, None, None, 16, 16, 1, 16, 64, 64, 64, 64, 64, 64, None) == -6       # no norm weight
+    assert lib.b200_linear_normw(16, 16, None, 16, 16, 16, 1, 16, 64, 256, 64, 64, 64, 256, None) == -1       # capacity < N / 64
+    assert lib.b200_attn_fwd_qnorm(16, 16, 16, 16, 1, 1, 8, 8, 128, *([8] * 12), 1.0, None, 1, 128, 1e-6, None) == -6
+    assert lib.b200_conv3d_cl_norm_silu(16, 16, None, 16, 16, 2, 8, 8, 64, 384, 3, 3, 3, None) == -1          # 384 = two N tiles
+    assert lib.b200_conv3d_cl_norm_silu(16, 16, None, None, 16, 2, 8, 8, 64, 96, 3, 3, 3, None) == -6         # no gamma
+    assert lib.b200_attn_fwd_scatter_joint(16, 16, 16, 2, 64, 64, 128, 128, 256, 128, 256, 128, 256, None, 2, 32, 0, 128, 512,
+                                           8, 0, 1.0, None) == -6
 
 
 def test_ops_fail_loudly_without_cuda_tensors():

@@ -73,3 +73,25 @@ def test_frames_to_uint8_rejects_cpu_tensor():
 
     with pytest.raises(ValueError):
         frames_to_uint8(torch.zeros(3, 1, 2, 2, dtype=torch.bfloat16))
+
+
+def test_fused_norm_rule_and_tile_launch_count(monkeypatch):
+    """Which residual blocks run conv1 + norm2 + SiLU as one kernel (the rule shared by csrc/wan_vae.cu and vae/wan.py), and the
+    launch count the C entry reports for a production tile (base_dim 96, 21 latent frames)."""
+    from apex_studio_b200.vae.wan import conv_norm_fusable
+
+    assert conv_norm_fusable(96) and conv_norm_fusable(192) and conv_norm_fusable(32)
+    assert not conv_norm_fusable(384) and not conv_norm_fusable(100)     # two N tiles / not a multiple of 16
+    vae = AutoencoderKLWan().init_random_weights("cpu", seed=7)
+    res = [k for k in vae.w if k.endswith(".conv1.bias") and ".resnets." in k]
+    assert len(res) == 14
+    fused = sum(1 for k in res if vae.w[k].numel() <= 256)
+    shortcuts = sum(1 for k in vae.w if k.endswith("conv_shortcut.weight"))
+    temporal = sum(1 for t in vae.temporal_upsample if t)
+    T = 21
+    # post_quant + conv_in + conv_out + norm_out | residual blocks | shortcuts | mid attention (4 + 3 per frame) | 3 upsamplers
+    expect = 4 + (14 * 4 - fused) + shortcuts + (4 + 3 * T) + 3 * 2 + temporal
+    assert vae._tile_launches(T) == expect == 130
+    monkeypatch.setenv("B200_VAE_FUSE_NORM", "0")
+    assert not conv_norm_fusable(96)
+    assert vae._tile_launches(T) == expect + fused
