@@ -372,8 +372,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_store_commit();
           }
         }
-        if (p.epi == B200_EPI_NORMW && row_ok)
-          p.row_sumsq[static_cast<int64_t>(row) * p.n_parts + (QUAD ? tn * 2 + static_cast<int>(pair_id) : tn)] = ss;
+        if (p.epi == B200_EPI_NORMW && row_ok) {
+          const int part = QUAD ? tn * 2 + static_cast<int>(pair_id) : tn;
+          if (part < p.n_parts) p.row_sumsq[static_cast<int64_t>(row) * p.n_parts + part] = ss;   // (QUAD: an odd tile count leaves a phantom tile)
+        }
         continue;   // next half / tile
       }
 #pragma unroll 1
