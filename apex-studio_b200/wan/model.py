@@ -380,7 +380,7 @@ class WanTransformer3DModel(LoraHostMixin):
 
     # ------------------------------------------------------------------------------------ CUDA graph
     def enable_cuda_graph(self, enabled: bool = True) -> None:
-        """Replay the whole forward (13 launches x layers + glue) from ONE CUDA graph per input shape.  Every
+        """Replay the whole forward (12 launches x layers + glue) from ONE CUDA graph per input shape.  Every
         kernel goes through the C ABI on the current stream with host-built TMA descriptors passed by value, weights and
         workspaces are static, nothing synchronises with the host -> capture once (after two warm-up runs), replay for every
         later step, cond and uncond alike (the text embedding is a graph INPUT).  Bit-identical to eager execution
